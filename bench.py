@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- render throughput of the NeRF-W ray-marching hot path (BASELINE.json metric: render Mrays/s, 64+128).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mlp-mode bf16x3|bf16|fp32]
+
+A step = one synthetic 800x800 view (640 000 rays) rendered coarse(64) + fine(64+128) with random-init NeRF-W weights
+(BASELINE.json configs[1]).  `value` is timed with the rays already in HBM; `e2e` goes through the public API with the
+rays in pinned HOST memory and the rgb/depth images read back to the host inside the timed region.
+Under torchrun (N > 1) every rank renders its own view of the aligned spiral (weak scaling, no data-path collective);
+time is the max over ranks.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "depth-aware-shader-effects-for-nerf_b200")
+for _p in (PKG, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H = W = 800
+N_COARSE, N_IMPORTANCE = 64, 128
+NEAR, FAR = 2.0, 6.0
+FLOP_PER_SAMPLE = 1_063_936          # 2 x 531 968 MAC, un-padded
+SAMPLES_PER_RAY = N_COARSE + (N_COARSE + N_IMPORTANCE)   # 64 coarse + 192 fine MLP evaluations
+METRIC = "render Mrays/s (64+128 samples)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mlp-mode", default=os.environ.get("NERFW_MLP_MODE", "bf16x3"), choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--cpu-rays", type=int, default=int(os.environ.get("NERFW_CPU_SAMPLE_RAYS", "2048")),
+                    help="rays in the bounded CPU sample (cpu_baseline / --impl reference step)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, local, world
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms: float, world: int) -> float:
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def make_weights():
+    import nerfw_oracle as orc
+    sd = orc.make_state_dict(0)          # == torch.manual_seed(0); NeRF(Config()) of the reference
+    emb = torch.randn(32)
+    return sd, emb
+
+
+def cpu_sample(sd, emb, n_rays: int, pose: np.ndarray):
+    """The reference algorithm (oracle port: same torch-CPU ops, same cost) on a bounded sample of the SAME workload:
+    `n_rays` rays from the centre rows of the 800x800 view, coarse 64 + fine 192, all host threads."""
+    import nerfw_oracle as orc
+    from nerfw.camera import blender_focal
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    focal = blender_focal(W)
+    c2w = torch.from_numpy(pose)
+    rows = max(1, n_rays // W)
+    r0 = H // 2 - rows // 2
+    # rays of the selected rows only (same formula as the full view; rays_for_view builds whole images)
+    ro, rd = orc.rays_for_view(H, W, focal, c2w)
+    o = ro[r0:r0 + rows].reshape(-1, 3)[:n_rays].contiguous()
+    d = rd[r0:r0 + rows].reshape(-1, 3)[:n_rays].contiguous()
+    torch.manual_seed(1)
+    u = torch.rand(o.shape[0], N_IMPORTANCE)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        rgb, depth, ex = orc.render_hier(sd, sd, o, d, NEAR, FAR, N_COARSE, N_IMPORTANCE, emb=emb, perturb=False, u_rand=u)
+    dt = time.perf_counter() - t0
+    return o.shape[0], dt, cores, (o, d, u, rgb, depth, ex["acc"])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from nerfw.camera import aligned_spiral_poses
+    sd, emb = make_weights()
+    pose = aligned_spiral_poses(120, 2, "x", "chair")[0]
+    times = []
+    n = 0
+    cores = 1
+    for i in range(args.warmup + args.steps):
+        n, dt, cores, _ = cpu_sample(sd, emb, args.cpu_rays, pose)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = n * len(times) / total / 1e6
+    sample = f"{n} rays of the 800x800 view per step (centre rows), coarse 64 + fine 192, torch CPU ops == reference code path"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "800x800 view render, 64+128 samples, random-init NeRF-W (BASELINE.json configs[1])",
+                   "rays_per_step": n, "note": "CPU reference path: rank 0 only, bounded sample per step"},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import nerfw
+    from config import Config
+    from nerfw import ops
+    from nerfw.camera import aligned_spiral_poses, blender_focal
+
+    rank, local, world = dist_setup(args.gpus)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    peaks = load_peaks()
+    sd, emb = make_weights()
+    model = nerfw.NeRF(Config())
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    emb_d = emb.to(dev)
+    poses = aligned_spiral_poses(120, 2, "x", "chair")
+    focal = blender_focal(W)
+    pose = poses[(rank * 15) % 120]          # each rank renders its own view of the spiral (config 4 partitioning)
+    c2w = torch.from_numpy(pose)
+    mode = args.mlp_mode
+    n_rays = H * W
+
+    def render(o, d):
+        with torch.no_grad():
+            return nerfw.volume_render(model, o, d, NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb_d,
+                                       perturb=False, mlp_dtype=mode, generator=gen)
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ro, rd = nerfw.get_rays(H, W, focal, c2w.to(dev))
+    o_dev = ro.reshape(-1, 3).contiguous()
+    d_dev = rd.reshape(-1, 3).contiguous()
+    # host-side copies for the e2e leg (pinned)
+    o_host = o_dev.cpu().pin_memory()
+    d_host = d_dev.cpu().pin_memory()
+    rgb_host = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory()
+    depth_host = torch.empty((n_rays, 1), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        o = o_host.to(dev, non_blocking=True)
+        d = d_host.to(dev, non_blocking=True)
+        rgb, depth, _ = render(o, d)
+        rgb_host.copy_(rgb, non_blocking=True)
+        depth_host.copy_(depth, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        render(o_dev, d_dev)
+    e2e_step()
+    barrier(world)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident timing ---------------------------------------------------------------------------------
+    l0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    ev0.record()
+    for _ in range(args.steps):
+        out = render(o_dev, d_dev)
+    ev1.record()
+    barrier(world)
+    launches = ops.launch_count() - l0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1), world)
+    # ---- end to end: pinned host rays -> device -> render -> host images -------------------------------------------
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- dominant kernel (fine-pass MLP) on its own, CUDA events on the launching stream -------------------------
+    with torch.no_grad():
+        z_fine = out[2]["z_vals"].contiguous()
+        dn = ops.normalize_dirs(d_dev)
+        names, tensors = model.kernel_params()
+        pd = {n: t.detach() for n, t in zip(names, tensors)}
+        packed = model.packed_weights(names, tensors)
+        emb2 = emb_d.unsqueeze(0).contiguous()
+        roof = {}
+        for m in sorted({mode, "bf16"}):
+            mid = nerfw.models.resolve_mode(m)
+            for _ in range(2):
+                raw = ops.mlp_fwd(pd, packed, o_dev, dn, z_fine, emb2, mid)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(2, args.steps)
+            k0.record()
+            for _ in range(reps):
+                raw = ops.mlp_fwd(pd, packed, o_dev, dn, z_fine, emb2, mid)
+            k1.record()
+            torch.cuda.synchronize()
+            kms = k0.elapsed_time(k1) / reps
+            flops = FLOP_PER_SAMPLE * float(z_fine.numel())
+            ach = flops / (kms * 1e-3) / 1e12
+            roof[m] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                       "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                       "kernel": "mlp_tc_fwd_kernel" if m != "fp32" else "mlp_ffma_fwd_kernel",
+                       "kernel_ms": kms, "samples_per_launch": int(z_fine.numel()),
+                       "peak_source": f"bf16 dense sustained, {peaks['source']}",
+                       "note": ("bf16x3 issues 3 bf16 MMAs per algorithmic product, so frac <= 1/3 by construction"
+                                if m == "bf16x3" else "")}
+        # HBM-bound kernels on the same frame
+        comp0, comp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ops.composite_fwd(raw, z_fine)
+        comp0.record()
+        for _ in range(5):
+            ops.composite_fwd(raw, z_fine)
+        comp1.record()
+        torch.cuda.synchronize()
+        cms = comp0.elapsed_time(comp1) / 5
+        cbytes = z_fine.numel() * 24.0 + n_rays * 20.0
+        zc = out[2]["z_vals_coarse"].contiguous()
+        wc = out[2]["weights_coarse"][..., 0].contiguous()
+        ur = torch.rand((n_rays, N_IMPORTANCE), device=dev)
+        ops.sample_pdf(zc, wc, N_IMPORTANCE, ur)
+        comp0.record()
+        for _ in range(5):
+            ops.sample_pdf(zc, wc, N_IMPORTANCE, ur)
+        comp1.record()
+        torch.cuda.synchronize()
+        rms = comp0.elapsed_time(comp1) / 5
+        rbytes = n_rays * (3 * N_COARSE + 2 * N_IMPORTANCE) * 4.0
+        hbm = {"composite_fwd": {"bound": "hbm", "achieved": cbytes / (cms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                 "unit": "GB/s", "frac": cbytes / (cms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": cms},
+               "sample_pdf": {"bound": "hbm", "achieved": rbytes / (rms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                              "unit": "GB/s", "frac": rbytes / (rms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": rms}}
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on a bounded sample + parity of the same sample ----------------------------------------------
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline:
+        n_cpu, dt, cores, (oc, dc, u, rgb_o, depth_o, acc_o) = cpu_sample(sd, emb, args.cpu_rays, poses[0])
+        with torch.no_grad():
+            rgb_g, depth_g, ex_g = nerfw.volume_render(model, oc.to(dev), dc.to(dev), NEAR, FAR, N_COARSE, N_IMPORTANCE,
+                                                       appearance_embedding=emb_d, perturb=False, mlp_dtype=mode, u_rand=u)
+        parity = {"rays": n_cpu, "rgb_max_abs": float((rgb_g.cpu() - rgb_o).abs().max()),
+                  "depth_max_abs": float((depth_g.cpu() - depth_o).abs().max()),
+                  "acc_max_abs": float((ex_g["acc"].cpu() - acc_o).abs().max())}
+        cpu = {"value": n_cpu / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} rays (centre rows of the same 800x800 view), coarse 64 + fine 192, one pass, {dt:.1f} s"}
+
+    value = world * n_rays * args.steps / (ms_total * 1e-3) / 1e6
+    e2e_val = world * n_rays * args.steps / (e2e_ms * 1e-3) / 1e6
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16x3": "bf16x3 (fp32-parity split, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}[mode],
+        "data": "synthetic",
+        "config": {"workload": "800x800 view render, 64+128 samples, random-init NeRF-W (BASELINE.json configs[1])",
+                   "rays_per_step_per_gpu": n_rays, "mlp_evals_per_ray": SAMPLES_PER_RAY, "mlp_mode": mode,
+                   "call": "one whole-frame volume_render per step", "parallelism": f"rays/frames sharded x{world}, no collective",
+                   "l2": "per-step working set 2.6 GB of sample buffers >> 126 MB L2 (inputs larger than L2)"},
+        "e2e": {"value": e2e_val, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(o_host.numel() * 4 + d_host.numel() * 4),
+                "d2h_bytes_per_step": int(rgb_host.numel() * 4 + depth_host.numel() * 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof[mode],
+        "roofline_other": {**{f"mlp_{k}": v for k, v in roof.items() if k != mode}, **hbm},
+        "cpu_baseline": cpu,
+        "parity_vs_oracle": parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device visible; the nerfw hot path has no CPU fallback "
+                             "(use --impl reference for the CPU reference arm)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

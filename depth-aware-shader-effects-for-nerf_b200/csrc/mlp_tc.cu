@@ -1,0 +1,565 @@
+// K4 (tensor-core modes): the NeRF-W MLP forward as one persistent, warp-specialised tcgen05 kernel.
+// src/models.py:105-162, fused with ray-point generation (src/ray_utils.py:86) and positional encoding
+// (src/models.py:35-44).
+//
+// Per CTA (one per SM) and per tile of 128 samples:
+//   * 8 epilogue warps compute the encodings into shared memory (K-major, 128B-swizzled UMMA operand tiles);
+//   * one producer thread streams the pre-swizzled bf16 weight chunks (32 KB = 256 outputs x 64 inputs) from L2 into a
+//     4-stage shared-memory ring with cp.async.bulk (TMA engine) + mbarrier transaction counts;
+//   * one MMA thread issues tcgen05.mma kind::f16 (M=128, N=256|128, K=16) with the accumulator in TMEM columns
+//     [0,256).  Layer inputs that are encodings come from shared memory (SS form); hidden activations never leave
+//     tensor memory: the epilogue warps read the fp32 accumulator (tcgen05.ld), add bias, ReLU, round to bf16 and
+//     write the next layer's A operand straight back into TMEM columns [256,384) (tcgen05.st; TS form);
+//   * the 1-wide density head and the 3-wide rgb head are fp32 dot products on CUDA cores inside the epilogues.
+//
+// NERFW_MLP_BF16X3 ("fp32 parity" mode): every operand is split x = hi + lo with hi = bf16(x), lo = bf16(x - hi) and
+// each product is three MMAs  A_hi W_hi + A_lo W_hi + A_hi W_lo  (dropped term ~2^-18): ~2^-16 relative error per
+// product against 2^-9 for plain bf16 and 2^-11 for TF32.  A_lo lives in TMEM columns [384,512).
+#include "common.cuh"
+#include "mlp_common.cuh"
+#include "mlp_tc.cuh"
+#include "umma.cuh"
+
+namespace nerfw {
+namespace tc {
+
+using namespace umma;
+
+constexpr int TM = 128;
+constexpr int EPI_WARPS = 8;
+constexpr int PRODUCER_WARP = 8;
+constexpr int MMA_WARP = 9;
+constexpr int THREADS = 320;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+
+constexpr uint32_t BIG_CHUNK = 256 * 128;    // 256 outputs x 64 bf16
+constexpr uint32_t SMALL_CHUNK = 128 * 128;  // 128 outputs x 64 bf16
+constexpr int N_BIG = 30;                    // L0:1, L1-3:12, L4:4+1, L5-7:12
+constexpr int N_SMALL = 5;                   // dir layer: 4 + 1
+constexpr int N_CHUNKS = N_BIG + N_SMALL;
+constexpr size_t W_BYTES = 2ull * (N_BIG * (size_t)BIG_CHUNK + N_SMALL * (size_t)SMALL_CHUNK);  // hi and lo
+
+// fp32 vector block behind the weight chunks
+constexpr int V_PTSB = 0;       // 8 x 256
+constexpr int V_DIRB = 2048;    // 128
+constexpr int V_DENW = 2176;    // 256
+constexpr int V_RGBW = 2432;    // 3 x 128
+constexpr int V_DENB = 2816;    // 1
+constexpr int V_RGBB = 2817;    // 3
+constexpr int V_FLOATS = 2824;  // padded to 16 B
+constexpr size_t PACKED_BYTES = W_BYTES + V_FLOATS * sizeof(float);
+
+// TMEM columns
+constexpr uint32_t COL_ACC = 0;
+constexpr uint32_t COL_AHI = 256;
+constexpr uint32_t COL_ALO = 384;
+
+// shared memory map (offsets from a 1024-aligned base)
+constexpr int NSTAGES = 4;
+constexpr uint32_t SM_PEX_HI = 0;
+constexpr uint32_t SM_PEX_LO = 16384;
+constexpr uint32_t SM_PED_HI = 32768;
+constexpr uint32_t SM_PED_LO = 49152;
+constexpr uint32_t SM_RING = 65536;
+constexpr uint32_t SM_VEC = SM_RING + NSTAGES * BIG_CHUNK;        // 196608
+constexpr uint32_t SM_SIG = SM_VEC + V_FLOATS * 4;                // [2][128] floats
+constexpr uint32_t SM_RGB = SM_SIG + 2 * TM * 4;                  // [128] float4
+constexpr uint32_t SM_BAR = SM_RGB + TM * 16;                     // full[4], empty[4], acc_full, a_ready
+constexpr uint32_t SM_TMEMPTR = SM_BAR + (2 * NSTAGES + 2) * 8;
+constexpr uint32_t SM_TOTAL = SM_TMEMPTR + 16;
+constexpr size_t SMEM_BYTES = SM_TOTAL + 1024;  // slack for the manual 1024-byte alignment
+
+// Chunk i of the stream -> (source matrix, first input column).  Order = consumption order of the MMA thread.
+struct ChunkSrc {
+  int layer;  // 0..7 trunk, 8 = dir layer
+  int col0;   // first input column of this 64-wide K block
+};
+__host__ __device__ inline ChunkSrc chunk_source(int i) {
+  if (i == 0) return {0, 0};
+  if (i < 13) return {1 + (i - 1) / 4, ((i - 1) % 4) * 64};
+  if (i < 18) return {4, (i - 13) * 64};  // i == 17: columns 256.. = enc_x part of the skip layer
+  if (i < 30) return {5 + (i - 18) / 4, ((i - 18) % 4) * 64};
+  return {8, (i - 30) * 64};              // i == 34: columns 256.. = enc_d part
+}
+__host__ __device__ inline size_t chunk_offset(int i) {  // byte offset of the hi copy; lo follows at +size
+  return i < N_BIG ? 2ull * i * BIG_CHUNK : 2ull * N_BIG * BIG_CHUNK + 2ull * (i - N_BIG) * SMALL_CHUNK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing: state_dict fp32 [out,in] -> bf16 hi/lo chunks in the exact shared-memory image (128B swizzle)
+__global__ void __launch_bounds__(256) pack_weights_kernel(NerfwWeights w, uint8_t* __restrict__ packed) {
+  // one thread per (chunk, output row, 8-wide k group)
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t big_items = (int64_t)N_BIG * 256 * 8;
+  const int64_t total = big_items + (int64_t)N_SMALL * 128 * 8;
+  if (idx < total) {
+    int chunk, n, g;
+    if (idx < big_items) {
+      chunk = (int)(idx / (256 * 8));
+      int r = (int)(idx % (256 * 8));
+      n = r / 8; g = r % 8;
+    } else {
+      int64_t j = idx - big_items;
+      chunk = N_BIG + (int)(j / (128 * 8));
+      int r = (int)(j % (128 * 8));
+      n = r / 8; g = r % 8;
+    }
+    ChunkSrc cs = chunk_source(chunk);
+    const float* W;
+    int K;
+    if (cs.layer == 8) { W = w.dir_w; K = 256 + NERFW_DIR_DIM; }
+    else { W = w.pts_w[cs.layer]; K = cs.layer == 0 ? NERFW_POS_DIM : (cs.layer == NERFW_SKIP ? 256 + NERFW_POS_DIM : 256); }
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int col = cs.col0 + g * 8 + e;
+      float v = col < K ? __ldg(W + (size_t)n * K + col) : 0.f;
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[e] = h;
+      lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+    const uint32_t sz = chunk < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
+    uint8_t* base = packed + chunk_offset(chunk);
+    uint32_t off = sw128_offset((uint32_t)n, (uint32_t)g * 8);
+    *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + sz + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+  // vector block
+  float* vec = reinterpret_cast<float*>(packed + W_BYTES);
+  for (int64_t v = idx; v < V_FLOATS; v += (int64_t)gridDim.x * blockDim.x) {
+    float x = 0.f;
+    if (v < V_DIRB) x = __ldg(w.pts_b[v / 256] + (v % 256));
+    else if (v < V_DENW) x = __ldg(w.dir_b + (v - V_DIRB));
+    else if (v < V_RGBW) x = __ldg(w.density_w + (v - V_DENW));
+    else if (v < V_DENB) x = __ldg(w.rgb_w + (v - V_RGBW));
+    else if (v == V_DENB) x = __ldg(w.density_b);
+    else if (v < V_RGBB + 3) x = __ldg(w.rgb_b + (v - V_RGBB));
+    vec[v] = x;
+  }
+}
+
+// appearance: off[row] = W_rgb (W_app e_row + b_app)  (src/models.py:146-160; the projection is added after the ReLU of
+// the direction layer, so its effect on the rgb logits is this per-embedding 3-vector).  One warp per row.
+__global__ void __launch_bounds__(128) app_offset_kernel(NerfwWeights w, const float* __restrict__ emb, int64_t rows,
+                                                         float4* __restrict__ out) {
+  int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float e = __ldg(emb + row * NERFW_APP_DIM + lane);  // APP_DIM == 32 == warp size
+  float o3[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < NERFW_DIR_HIDDEN; ++k) {
+    float p = __ldg(w.app_w + k * NERFW_APP_DIM + lane) * e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    float a = p + __ldg(w.app_b + k);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o3[c] = fmaf(__ldg(w.rgb_w + c * NERFW_DIR_HIDDEN + k), a, o3[c]);
+  }
+  if (lane == 0) out[row] = make_float4(o3[0], o3[1], o3[2], 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct Pipe {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+  }
+};
+
+// write one encoded value (hi and optionally lo) into a K-major swizzled operand tile
+template <bool X3>
+__device__ __forceinline__ void put_enc(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t row, uint32_t k, float v) {
+  uint32_t off = sw128_offset(row, k);
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(tile_hi + off) = h;
+  if (X3) *reinterpret_cast<__nv_bfloat16*>(tile_lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* __restrict__ packed, SampleSource src,
+                                                                 const float4* __restrict__ app_off, int64_t n_total,
+                                                                 float4* __restrict__ raw) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + SM_BAR);
+  uint64_t* empty = full + NSTAGES;
+  uint64_t* acc_full = empty + NSTAGES;
+  uint64_t* a_ready = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM_TMEMPTR);
+  float* vec = reinterpret_cast<float*>(sm + SM_VEC);
+  float* sig_part = reinterpret_cast<float*>(sm + SM_SIG);
+  float4* rgb_part = reinterpret_cast<float4*>(sm + SM_RGB);
+
+  if (warp == PRODUCER_WARP && lane == 0) {
+    for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(a_ready, EPI_THREADS);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc<512>(tmem_ptr);
+  if (warp < EPI_WARPS) {
+    const float* gv = reinterpret_cast<const float*>(packed + W_BYTES);
+    for (int i = tid; i < V_FLOATS; i += EPI_THREADS) vec[i] = __ldg(gv + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const int64_t ntiles = (n_total + TM - 1) / TM;
+
+  if (warp == PRODUCER_WARP) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      Pipe p;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        size_t off = 0;
+        for (int i = 0; i < N_CHUNKS; ++i) {
+          const uint32_t sz = i < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
+#pragma unroll
+          for (int v = 0; v < (X3 ? 2 : 1); ++v) {
+            mbar_wait(&empty[p.stage], p.phase ^ 1);
+            mbar_arrive_expect_tx(&full[p.stage], sz);
+            bulk_g2s(sm + SM_RING + p.stage * BIG_CHUNK, packed + off + (size_t)v * sz, sz, &full[p.stage]);
+            p.advance();
+          }
+          off += 2ull * sz;
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      Pipe p;
+      uint32_t ar_phase = 0;
+      const uint32_t idesc256 = idesc_bf16(128, 256), idesc128 = idesc_bf16(128, 128);
+      const uint32_t ring = smem_u32(sm + SM_RING);
+      const uint32_t d_acc = tmem + COL_ACC;
+      // one 64-wide K block: A (hi[,lo]) x W chunk (hi[,lo]); a_* are either TMEM addresses (TS) or smem descs (SS)
+      auto kblock = [&](bool from_tmem, uint64_t a_hi, uint64_t a_lo, uint32_t idesc, int ksteps, bool first) {
+        mbar_wait(&full[p.stage], p.phase);
+        tc_fence_after();
+        uint64_t b = smem_desc_sw128(ring + p.stage * BIG_CHUNK);
+        for (int k = 0; k < ksteps; ++k) {
+          uint32_t accf = (first && k == 0) ? 0u : 1u;
+          if (from_tmem) mma_ts(d_acc, (uint32_t)a_hi + 8 * k, b + 2 * k, idesc, accf);
+          else mma_ss(d_acc, a_hi + 2 * k, b + 2 * k, idesc, accf);
+        }
+        if (X3) {
+          for (int k = 0; k < ksteps; ++k) {
+            if (from_tmem) mma_ts(d_acc, (uint32_t)a_lo + 8 * k, b + 2 * k, idesc, 1u);
+            else mma_ss(d_acc, a_lo + 2 * k, b + 2 * k, idesc, 1u);
+          }
+        }
+        mma_commit(&empty[p.stage]);
+        p.advance();
+        if (X3) {
+          mbar_wait(&full[p.stage], p.phase);
+          tc_fence_after();
+          uint64_t bl = smem_desc_sw128(ring + p.stage * BIG_CHUNK);
+          for (int k = 0; k < ksteps; ++k) {
+            if (from_tmem) mma_ts(d_acc, (uint32_t)a_hi + 8 * k, bl + 2 * k, idesc, 1u);
+            else mma_ss(d_acc, a_hi + 2 * k, bl + 2 * k, idesc, 1u);
+          }
+          mma_commit(&empty[p.stage]);
+          p.advance();
+        }
+      };
+      const uint64_t pex_hi = smem_desc_sw128(smem_u32(sm + SM_PEX_HI)), pex_lo = smem_desc_sw128(smem_u32(sm + SM_PEX_LO));
+      const uint64_t ped_hi = smem_desc_sw128(smem_u32(sm + SM_PED_HI)), ped_lo = smem_desc_sw128(smem_u32(sm + SM_PED_LO));
+      auto wait_a = [&]() {
+        mbar_wait(a_ready, ar_phase);
+        ar_phase ^= 1;
+        tc_fence_after();
+      };
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
+          wait_a();
+          if (layer == 0) {
+            kblock(false, pex_hi, pex_lo, idesc256, 4, true);
+          } else {
+            for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc256, 4, kb == 0);
+            if (layer == NERFW_SKIP) kblock(false, pex_hi, pex_lo, idesc256, 4, false);
+          }
+          mma_commit(acc_full);
+        }
+        wait_a();
+        for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, kb == 0);
+        kblock(false, ped_hi, ped_lo, idesc128, 2, false);
+        mma_commit(acc_full);
+      }
+    }
+  } else {
+    // ===================== encoders + epilogues (8 warps, thread <-> sample row) =====================
+    const uint32_t quad = warp & 3, ch = warp >> 2;
+    const uint32_t row = quad * 32 + lane;
+    const uint32_t tlane = tmem + ((quad * 32) << 16);
+    uint32_t acc_phase = 0;
+    uint8_t* pex_hi = sm + SM_PEX_HI;
+    uint8_t* pex_lo = sm + SM_PEX_LO;
+    uint8_t* ped_hi = sm + SM_PED_HI;
+    uint8_t* ped_lo = sm + SM_PED_LO;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t s = tile * TM + row;
+      const bool live = s < n_total;
+      // ---- encodings.  ch 0: x and position levels 0..6;  ch 1: position levels 7..9 and the direction encoding ----
+      {
+        float x[3] = {0.f, 0.f, 0.f};
+        if (live) src.position(s, x);
+        if (ch == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) put_enc<X3>(pex_hi, pex_lo, row, c, x[c]);
+        } else {
+          put_enc<X3>(pex_hi, pex_lo, row, 63, 0.f);
+        }
+        const int l0 = ch == 0 ? 0 : 7, l1 = ch == 0 ? 7 : NERFW_POS_LEVELS;
+        for (int l = l0; l < l1; ++l) {
+          float f = (float)(1u << l);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sn, cs;
+            sincosf(f * x[c], &sn, &cs);
+            put_enc<X3>(pex_hi, pex_lo, row, 3 + 6 * l + c, sn);
+            put_enc<X3>(pex_hi, pex_lo, row, 6 + 6 * l + c, cs);
+          }
+        }
+        if (ch == 1) {
+          float d[3] = {0.f, 0.f, 0.f};
+          if (live) src.direction(s, d);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) put_enc<X3>(ped_hi, ped_lo, row, c, d[c]);
+          for (int l = 0; l < NERFW_DIR_LEVELS; ++l) {
+            float f = (float)(1u << l);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float sn, cs;
+              sincosf(f * d[c], &sn, &cs);
+              put_enc<X3>(ped_hi, ped_lo, row, 3 + 6 * l + c, sn);
+              put_enc<X3>(ped_hi, ped_lo, row, 6 + 6 * l + c, cs);
+            }
+          }
+          for (int k = NERFW_DIR_DIM; k < 32; ++k) put_enc<X3>(ped_hi, ped_lo, row, k, 0.f);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(a_ready);
+
+      // ---- trunk epilogues: acc -> bias, ReLU -> bf16 (hi[,lo]) -> next layer's A operand in TMEM ----
+      float sig = 0.f;
+      for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
+        mbar_wait(acc_full, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const float* bias = vec + V_PTSB + layer * 256;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t col = ch * 128 + q * 32;
+          uint32_t r[32];
+          tmem_ld32(tlane + COL_ACC + col, r);
+          tmem_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bias[col + j], 0.f);
+          if (layer == NERFW_LAYERS - 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sig = fmaf(v[j], vec[V_DENW + col + j], sig);
+          }
+          uint32_t ph[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          tmem_st16(tlane + COL_AHI + (col >> 1), ph);
+          if (X3) {
+            uint32_t pl[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float l0v = v[2 * j] - __uint_as_float(ph[j] << 16);
+              float l1v = v[2 * j + 1] - __uint_as_float(ph[j] & 0xffff0000u);
+              pl[j] = pack_bf16x2(l0v, l1v);
+            }
+            tmem_st16(tlane + COL_ALO + (col >> 1), pl);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+      }
+      sig_part[ch * TM + row] = sig;
+
+      // ---- direction-layer epilogue + rgb head (src/models.py:141-160) ----
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      float p3[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t col = ch * 64 + q * 32;
+        uint32_t r[32];
+        tmem_ld32(tlane + COL_ACC + col, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float hv = fmaxf(__uint_as_float(r[j]) + vec[V_DIRB + col + j], 0.f);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv, vec[V_RGBW + c * 128 + col + j], p3[c]);
+        }
+      }
+      tc_fence_before();
+      if (ch == 1) rgb_part[row] = make_float4(p3[0], p3[1], p3[2], 0.f);
+      named_bar_sync(1, EPI_THREADS);
+      if (ch == 0 && live) {
+        float4 other = rgb_part[row];
+        float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (app_off) off = __ldg(app_off + src.emb_row(s));
+        float sg = sig_part[row] + sig_part[TM + row] + vec[V_DENB];
+        float4 o;
+        o.x = 1.0f / (1.0f + expf(-(p3[0] + other.x + vec[V_RGBB + 0] + off.x)));
+        o.y = 1.0f / (1.0f + expf(-(p3[1] + other.y + vec[V_RGBB + 1] + off.y)));
+        o.z = 1.0f / (1.0f + expf(-(p3[2] + other.z + vec[V_RGBB + 2] + off.z)));
+        o.w = fmaxf(sg, 0.f);
+        raw[s] = o;
+      }
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Self-test of the primitives: D (128 x N fp32) = A (128 x K bf16) * B (N x K bf16)^T for one CTA.
+// mode 0: A from shared memory (SS); mode 1: A from tensor memory (TS).  K multiple of 64 (<= 256), N multiple of 16.
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat16* __restrict__ A,
+                                                               const __nv_bfloat16* __restrict__ B, int N, int K, int mode,
+                                                               float* __restrict__ D) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  uint8_t* sA = sm;                  // K/64 tiles of 128 x 128 B
+  uint8_t* sB = sm + 65536;          // K/64 tiles of N x 128 B (256*128 stride)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 65536 + 131072);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = K / 64;
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  // stage operands
+  for (int idx = tid; idx < N * K; idx += 128) {
+    int n = idx / K, k = idx % K;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (k / 64) * BIG_CHUNK + sw128_offset(n, k % 64)) = B[idx];
+  }
+  if (mode == 0) {
+    for (int idx = tid; idx < 128 * K; idx += 128) {
+      int m = idx / K, k = idx % K;
+      *reinterpret_cast<__nv_bfloat16*>(sA + (k / 64) * 16384 + sw128_offset(m, k % 64)) = A[idx];
+    }
+  } else {
+    const uint32_t tl = tmem + ((warp * 32) << 16);
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t pk[16];
+      for (int j = 0; j < 16; ++j) {
+        const __nv_bfloat16* a = A + (size_t)tid * K + 2 * (c0 + j);
+        pk[j] = (uint32_t)__bfloat16_as_ushort(a[0]) | ((uint32_t)__bfloat16_as_ushort(a[1]) << 16);
+      }
+      tmem_st16(tl + COL_AHI + c0, pk);
+    }
+    tmem_wait_st();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16(128, (uint32_t)N);
+    for (int kb = 0; kb < nkb; ++kb) {
+      uint64_t b = smem_desc_sw128(smem_u32(sB + kb * BIG_CHUNK));
+      uint64_t a = smem_desc_sw128(smem_u32(sA + kb * 16384));
+      for (int k = 0; k < 4; ++k) {
+        uint32_t accf = (kb | k) ? 1u : 0u;
+        if (mode == 0) mma_ss(tmem + COL_ACC, a + 2 * k, b + 2 * k, idesc, accf);
+        else mma_ts(tmem + COL_ACC, tmem + COL_AHI + 32 * kb + 8 * k, b + 2 * k, idesc, accf);
+      }
+    }
+    mma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  {
+    const uint32_t tl = tmem + ((warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tl + COL_ACC + c0, r);
+      tmem_wait_ld();
+      for (int j = 0; j < 32 && c0 + j < N; ++j) D[(size_t)tid * N + c0 + j] = __uint_as_float(r[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace tc
+
+size_t mlp_tc_packed_bytes() { return tc::PACKED_BYTES; }
+
+int launch_pack_weights(const NerfwWeights& w, void* packed, cudaStream_t stream) {
+  const int64_t total = (int64_t)tc::N_BIG * 256 * 8 + (int64_t)tc::N_SMALL * 128 * 8;
+  tc::pack_weights_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(packed));
+  NERFW_LAUNCHED();
+  return NERFW_OK;
+}
+
+int launch_app_offset(const NerfwWeights& w, const float* emb, int64_t emb_rows, float* app_off, cudaStream_t stream) {
+  tc::app_offset_kernel<<<(unsigned)ceil_div64(emb_rows, 4), 128, 0, stream>>>(w, emb, emb_rows, reinterpret_cast<float4*>(app_off));
+  NERFW_LAUNCHED();
+  return NERFW_OK;
+}
+
+int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSource& src, const float* app_off,
+                      int64_t n_total, bool x3, float* raw, cudaStream_t stream) {
+  (void)w;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  int64_t ntiles = ceil_div64(n_total, tc::TM);
+  int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  const float4* ao = reinterpret_cast<const float4*>(app_off);
+  if (x3)
+    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw));
+  else
+    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw));
+  NERFW_LAUNCHED();
+  return NERFW_OK;
+}
+
+}  // namespace nerfw
+
+// D = A B^T through tcgen05 for one 128-row tile; used by tests to pin descriptor / swizzle / TMEM layouts.
+extern "C" int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream) {
+  using namespace nerfw;
+  NERFW_REQUIRE(a_bf16 && b_bf16 && d, "nerfw_selftest_umma: null pointer");
+  NERFW_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "nerfw_selftest_umma: N must be a multiple of 16 in [16,256]");
+  NERFW_REQUIRE(k >= 64 && k <= 256 && k % 64 == 0, "nerfw_selftest_umma: K must be a multiple of 64 in [64,256]");
+  NERFW_REQUIRE(mode == 0 || mode == 1, "nerfw_selftest_umma: mode must be 0 (SS) or 1 (TS)");
+  const size_t smem = 65536 + 131072 + 64 + 1024;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    NERFW_CUDA(cudaFuncSetAttribute(tc::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tc::umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(a_bf16),
+                                                               reinterpret_cast<const __nv_bfloat16*>(b_bf16), n, k, mode, d);
+  NERFW_LAUNCHED();
+  return NERFW_OK;
+}

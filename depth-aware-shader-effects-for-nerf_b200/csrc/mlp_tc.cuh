@@ -1,0 +1,13 @@
+// Tensor-core (tcgen05) MLP: host-side launchers shared with mlp_api.cu.
+#pragma once
+#include "common.cuh"
+#include "mlp_common.cuh"
+
+namespace nerfw {
+size_t mlp_tc_packed_bytes();
+int launch_pack_weights(const NerfwWeights& w, void* packed, cudaStream_t stream);
+int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSource& src, const float* app_off,
+                      int64_t n_total, bool x3, float* raw, cudaStream_t stream);
+// rgb-logit offset of the appearance embedding, one float4 per embedding row: W_rgb (W_app e + b_app)
+int launch_app_offset(const NerfwWeights& w, const float* emb, int64_t emb_rows, float* app_off, cudaStream_t stream);
+}  // namespace nerfw

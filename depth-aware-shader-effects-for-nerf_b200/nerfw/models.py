@@ -1,0 +1,140 @@
+"""NeRF-W model with the reference's interface and parameter layout (src/models.py:6-162), forward/backward on sm_100a.
+
+`NeRF(config)` builds the same `nn.Linear` submodules in the same order as the reference (src/models.py:80-103), so
+`state_dict()` keys/shapes match, existing checkpoints load with strict=True and `torch.manual_seed(s); NeRF(cfg)`
+yields the same initial weights.  The nn.Linear modules only own the parameters; the arithmetic is the fused CUDA MLP.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import MODE_NAMES
+from .autograd import MlpFn
+
+DEFAULT_MLP_MODE = os.environ.get("NERFW_MLP_MODE", "bf16x3")
+
+
+def resolve_mode(mode: Optional[str]) -> int:
+    name = (mode or DEFAULT_MLP_MODE).lower()
+    if name not in MODE_NAMES:
+        raise ValueError(f"mlp_dtype must be one of {sorted(MODE_NAMES)}, got {mode!r}")
+    return MODE_NAMES[name]
+
+
+class PositionalEncoding:
+    """[x, sin(2^0 x), cos(2^0 x), ...] -- src/models.py:6-54 (same constructor, __call__ and output_dim)."""
+
+    def __init__(self, num_frequencies, include_input=True):
+        self.num_frequencies = num_frequencies
+        self.include_input = include_input
+
+    def __call__(self, x):
+        if not x.is_cuda:
+            raise ValueError("PositionalEncoding: input must be a CUDA tensor; the nerfw kernels have no CPU path")
+        return ops.posenc(x, self.num_frequencies, self.include_input)
+
+    def output_dim(self, input_dim):
+        if self.include_input:
+            return input_dim * (1 + 2 * self.num_frequencies)
+        return input_dim * 2 * self.num_frequencies
+
+
+class NeRF(nn.Module):
+    """Drop-in for src/models.py:57-162.  Reads the same config attributes (src/models.py:69-101)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        unsupported = []
+        if config.hidden_dim != 256: unsupported.append(f"hidden_dim={config.hidden_dim} (256)")
+        if config.num_layers != 8: unsupported.append(f"num_layers={config.num_layers} (8)")
+        if list(config.skip_connect_layers) != [4]: unsupported.append(f"skip_connect_layers={config.skip_connect_layers} ([4])")
+        if config.pos_enc_levels != 10: unsupported.append(f"pos_enc_levels={config.pos_enc_levels} (10)")
+        if config.dir_enc_levels != 4: unsupported.append(f"dir_enc_levels={config.dir_enc_levels} (4)")
+        if getattr(config, "use_appearance", False) and config.appearance_dim != 32:
+            unsupported.append(f"appearance_dim={config.appearance_dim} (32)")
+        if unsupported:
+            raise ValueError("the sm_100a NeRF-W kernels are specialised for the reference architecture; unsupported: "
+                             + ", ".join(unsupported) + ".  There is no generic fallback.")
+        self.pos_encoder = PositionalEncoding(config.pos_enc_levels)
+        self.dir_encoder = PositionalEncoding(config.dir_enc_levels)
+        pos_enc_dim = 3 * (1 + 2 * config.pos_enc_levels)
+        dir_enc_dim = 3 * (1 + 2 * config.dir_enc_levels)
+        self.pts_linears = nn.ModuleList()
+        self.pts_linears.append(nn.Linear(pos_enc_dim, config.hidden_dim))
+        for i in range(1, config.num_layers):
+            if i in config.skip_connect_layers:
+                self.pts_linears.append(nn.Linear(config.hidden_dim + pos_enc_dim, config.hidden_dim))
+            else:
+                self.pts_linears.append(nn.Linear(config.hidden_dim, config.hidden_dim))
+        self.density_head = nn.Linear(config.hidden_dim, 1)
+        self.dir_linear = nn.Linear(config.hidden_dim + dir_enc_dim, config.hidden_dim // 2)
+        if config.use_appearance:
+            self.appearance_projection = nn.Linear(config.appearance_dim, config.hidden_dim // 2)
+        self.rgb_linear = nn.Linear(config.hidden_dim // 2, 3)
+        self.mlp_mode: Optional[str] = None  # None -> DEFAULT_MLP_MODE / per-call override
+        self._packed = None
+        self._packed_key = None
+
+    # ---- kernel-facing views of the parameters -------------------------------------------------------------
+    def kernel_params(self):
+        names, tensors = [], []
+        for n, p in self.named_parameters():
+            names.append(n)
+            tensors.append(p)
+        return tuple(names), tensors
+
+    def packed_weights(self, names, tensors):
+        """bf16 hi/lo weight image for the tcgen05 kernel; rebuilt whenever a parameter changed (derived cache)."""
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._packed is None or key != self._packed_key or self._packed.device != tensors[0].device:
+            pd = {n: t.detach() for n, t in zip(names, tensors)}
+            ops.check_params(pd)
+            self._packed = ops.pack_weights(pd, self._packed if (self._packed is not None and self._packed.device == tensors[0].device) else None)
+            self._packed_key = key
+        return self._packed
+
+    def run_mlp(self, p, d, z, emb, mode: Optional[str] = None):
+        """raw (S,4) for samples (z None) or rays (z (B,N)); differentiable wrt parameters and emb."""
+        mode_id = resolve_mode(mode or self.mlp_mode)
+        names, tensors = self.kernel_params()
+        dev = tensors[0].device
+        if not dev.type == "cuda":
+            raise RuntimeError("NeRF: parameters are on %s; move the model to a CUDA (sm_100) device -- no CPU path exists" % dev)
+        ops.require_device(dev)
+        packed = self.packed_weights(names, tensors) if mode_id != 0 else None
+        if mode_id == 0:
+            ops.check_params({n: t.detach() for n, t in zip(names, tensors)})
+        needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or (emb is not None and emb.requires_grad))
+        if needs_grad:
+            return MlpFn.apply(mode_id, names, p, d, z, emb, packed, *tensors)
+        return ops.mlp_fwd({n: t.detach() for n, t in zip(names, tensors)}, packed, p, d, z,
+                           None if emb is None else emb.detach(), mode_id)
+
+    def _prep_emb(self, appearance_embedding, rows, device):
+        if appearance_embedding is None or not getattr(self.config, "use_appearance", False):
+            return None
+        e = appearance_embedding
+        if e.dim() == 1:
+            e = e.unsqueeze(0)
+        if e.shape[0] != 1 and e.shape[0] != rows:
+            raise ValueError(f"appearance_embedding has {e.shape[0]} rows; expected 1 or {rows}")
+        if e.shape[-1] != 32:
+            raise ValueError(f"appearance_embedding must have 32 features, got {e.shape[-1]}")
+        return e.to(device=device, dtype=torch.float32).contiguous()
+
+    def forward(self, x, d, appearance_embedding=None):
+        """(rgb (S,3), sigma (S,1)) -- src/models.py:105-162."""
+        dev = self.rgb_linear.weight.device
+        x = x.to(dev, torch.float32).reshape(-1, 3).contiguous()
+        d = d.to(dev, torch.float32).reshape(-1, 3).contiguous()
+        if x.shape != d.shape:
+            raise ValueError(f"x {tuple(x.shape)} and d {tuple(d.shape)} must have the same shape")
+        emb = self._prep_emb(appearance_embedding, x.shape[0], dev)
+        raw = self.run_mlp(x, d, None, emb)
+        return raw[:, :3], raw[:, 3:4]

@@ -1,0 +1,321 @@
+"""Tensor-level wrappers over the C ABI (include/nerfw.h).
+
+Every function takes/returns torch CUDA tensors, allocates outputs with the torch caching allocator, enqueues on
+torch's current stream and never synchronises.  Inputs that are not CUDA / float32 / contiguous are rejected or
+made contiguous here; nothing in this module computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_ZTAB_CACHE: dict = {}
+_ULIN_CACHE: dict = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (got {t.device}); the nerfw kernels have no CPU path")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+_device_checked = set()
+
+
+def require_device(device: torch.device) -> None:
+    """Fail loudly unless `device` is an sm_100 GPU (no fallback)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _device_checked:
+        return
+    with torch.cuda.device(idx):
+        check(lib().nerfw_check_device())
+    _device_checked.add(idx)
+
+
+def launch_count() -> int:
+    return int(lib().nerfw_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------ rays
+def raygen(height: int, width: int, focal: float, c2w: torch.Tensor, device: torch.device,
+           want_origins: bool = True) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+    require_device(device)
+    c = c2w.detach().to("cpu", torch.float32)
+    if c.shape[-2:] not in ((4, 4), (3, 4)):
+        raise ValueError(f"c2w must be (4,4) or (3,4), got {tuple(c2w.shape)}")
+    host = (C.c_float * 12)(*c[:3, :4].reshape(-1).tolist())
+    with torch.cuda.device(device):
+        dirs = torch.empty((height, width, 3), dtype=torch.float32, device=device)
+        origins = torch.empty((height, width, 3), dtype=torch.float32, device=device) if want_origins else None
+        # `focal` arrives as a python/numpy double; the reference's tensor/scalar division rounds it to fp32 first
+        check(lib().nerfw_raygen(int(height), int(width), float(torch.tensor(float(focal), dtype=torch.float32)),
+                                 host, _ptr(origins), dirs.data_ptr(), _stream()))
+    return origins, dirs
+
+
+def normalize_dirs(d: torch.Tensor) -> torch.Tensor:
+    d = _f32c(d, "rays_d")
+    out = torch.empty_like(d)
+    with torch.cuda.device(d.device):
+        check(lib().nerfw_normalize_dirs(d.data_ptr(), d.numel() // 3, out.data_ptr(), _stream()))
+    return out
+
+
+def depth_table(near: float, far: float, n: int, device: torch.device) -> torch.Tensor:
+    """near + linspace(0,1,N)*(far-near) computed with HOST torch (bit-identical to src/ray_utils.py:69-70), cached."""
+    key = (float(near), float(far), int(n), str(device))
+    tab = _ZTAB_CACHE.get(key)
+    if tab is None:
+        t = torch.linspace(0.0, 1.0, int(n))
+        tab = (near + t * (far - near)).to(device)
+        _ZTAB_CACHE[key] = tab
+    return tab
+
+
+def u_table(n_importance: int, device: torch.device) -> torch.Tensor:
+    """linspace(0,1,NI+1)[:-1] from host torch (src/ray_utils.py:115), cached."""
+    key = (int(n_importance), str(device))
+    tab = _ULIN_CACHE.get(key)
+    if tab is None:
+        tab = torch.linspace(0.0, 1.0, int(n_importance) + 1)[:-1].contiguous().to(device)
+        _ULIN_CACHE[key] = tab
+    return tab
+
+
+def stratified(rays_o: Optional[torch.Tensor], rays_d: Optional[torch.Tensor], ztab: torch.Tensor,
+               t_rand: Optional[torch.Tensor], n_rays: int, want_pts: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    n = ztab.numel()
+    dev = ztab.device
+    z = torch.empty((n_rays, n), dtype=torch.float32, device=dev)
+    pts = torch.empty((n_rays, n, 3), dtype=torch.float32, device=dev) if want_pts else None
+    if t_rand is not None:
+        t_rand = _f32c(t_rand, "t_rand")
+        if tuple(t_rand.shape) != (n_rays, n):
+            raise ValueError(f"t_rand must be ({n_rays},{n}), got {tuple(t_rand.shape)}")
+    with torch.cuda.device(dev):
+        check(lib().nerfw_stratified(_ptr(rays_o), _ptr(rays_d), ztab.data_ptr(), _ptr(t_rand), n_rays, n,
+                                     z.data_ptr(), _ptr(pts), _stream()))
+    return z, pts
+
+
+def ray_points(rays_o: torch.Tensor, rays_d: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    b, n = z.shape
+    pts = torch.empty((b, n, 3), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        check(lib().nerfw_ray_points(rays_o.data_ptr(), rays_d.data_ptr(), z.data_ptr(), b, n, pts.data_ptr(), _stream()))
+    return pts
+
+
+def sample_pdf(z_vals: torch.Tensor, weights: torch.Tensor, n_importance: int, u_rand: torch.Tensor,
+               want_aux: bool = False):
+    z_vals = _f32c(z_vals, "z_vals")
+    weights = _f32c(weights, "weights")
+    u_rand = _f32c(u_rand, "u_rand")
+    b, n = z_vals.shape
+    if tuple(weights.shape) != (b, n):
+        raise ValueError(f"weights must be ({b},{n}), got {tuple(weights.shape)}")
+    if tuple(u_rand.shape) != (b, n_importance):
+        raise ValueError(f"u_rand must be ({b},{n_importance}), got {tuple(u_rand.shape)}")
+    dev = z_vals.device
+    out = torch.empty((b, n + n_importance), dtype=torch.float32, device=dev)
+    inds = zf = cdf = None
+    if want_aux:
+        inds = torch.empty((b, n_importance), dtype=torch.int64, device=dev)
+        zf = torch.empty((b, n_importance), dtype=torch.float32, device=dev)
+        cdf = torch.empty((b, n + 1), dtype=torch.float32, device=dev)
+    ulin = u_table(n_importance, dev)
+    with torch.cuda.device(dev):
+        check(lib().nerfw_sample_pdf(z_vals.data_ptr(), weights.data_ptr(), ulin.data_ptr(), u_rand.data_ptr(), b, n,
+                                     int(n_importance), out.data_ptr(), _ptr(inds), _ptr(zf), _ptr(cdf), _stream()))
+    if want_aux:
+        return out, {"inds": inds, "z_fine": zf, "cdf": cdf}
+    return out
+
+
+def posenc(x: torch.Tensor, levels: int, include_input: bool = True) -> torch.Tensor:
+    x = _f32c(x, "x")
+    dim = x.shape[-1]
+    lead = x.shape[:-1]
+    flat = x.reshape(-1, dim)
+    width = dim * ((1 if include_input else 0) + 2 * levels)
+    out = torch.empty((flat.shape[0], width), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().nerfw_posenc(flat.data_ptr(), flat.shape[0], dim, int(levels), int(bool(include_input)),
+                                 out.data_ptr(), _stream()))
+    return out.reshape(*lead, width)
+
+
+# ------------------------------------------------------------------------------------------------ MLP
+PARAM_ORDER = ([f"pts_linears.{i}.weight" for i in range(8)] + [f"pts_linears.{i}.bias" for i in range(8)] +
+               ["density_head.weight", "density_head.bias", "dir_linear.weight", "dir_linear.bias",
+                "appearance_projection.weight", "appearance_projection.bias", "rgb_linear.weight", "rgb_linear.bias"])
+
+EXPECTED_SHAPES = {
+    **{f"pts_linears.{i}.weight": (256, 63 if i == 0 else (319 if i == 4 else 256)) for i in range(8)},
+    **{f"pts_linears.{i}.bias": (256,) for i in range(8)},
+    "density_head.weight": (1, 256), "density_head.bias": (1,),
+    "dir_linear.weight": (128, 283), "dir_linear.bias": (128,),
+    "appearance_projection.weight": (128, 32), "appearance_projection.bias": (128,),
+    "rgb_linear.weight": (3, 128), "rgb_linear.bias": (3,),
+}
+
+
+def weights_struct(params: dict) -> _lib.NerfwWeights:
+    """Fill NerfwWeights/NerfwGrads from {state_dict key: contiguous fp32 CUDA tensor}.  Missing appearance -> NULL."""
+    s = _lib.NerfwWeights()
+    for i in range(8):
+        s.pts_w[i] = params[f"pts_linears.{i}.weight"].data_ptr()
+        s.pts_b[i] = params[f"pts_linears.{i}.bias"].data_ptr()
+    s.density_w = params["density_head.weight"].data_ptr()
+    s.density_b = params["density_head.bias"].data_ptr()
+    s.dir_w = params["dir_linear.weight"].data_ptr()
+    s.dir_b = params["dir_linear.bias"].data_ptr()
+    aw = params.get("appearance_projection.weight")
+    ab = params.get("appearance_projection.bias")
+    s.app_w = aw.data_ptr() if aw is not None else None
+    s.app_b = ab.data_ptr() if ab is not None else None
+    s.rgb_w = params["rgb_linear.weight"].data_ptr()
+    s.rgb_b = params["rgb_linear.bias"].data_ptr()
+    return s
+
+
+def check_params(params: dict) -> None:
+    for k, t in params.items():
+        exp = EXPECTED_SHAPES.get(k)
+        if exp is None:
+            raise ValueError(f"unexpected parameter {k}")
+        if tuple(t.shape) != exp:
+            raise ValueError(
+                f"{k} has shape {tuple(t.shape)}; the sm_100a kernels are specialised for the reference architecture "
+                f"(hidden 256, 8 layers, skip [4], L=10/4, appearance 32) and expect {exp}.  No fallback exists.")
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{k} must be a contiguous float32 CUDA tensor (got {t.dtype} on {t.device})")
+
+
+def packed_bytes() -> int:
+    return int(lib().nerfw_packed_bytes())
+
+
+def pack_weights(params: dict, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = params["rgb_linear.weight"].device
+    nbytes = packed_bytes()
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ws = weights_struct(params)
+    with torch.cuda.device(dev):
+        check(lib().nerfw_pack_weights(C.byref(ws), out.data_ptr(), out.numel(), _stream()))
+    return out
+
+
+def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: torch.Tensor, z: Optional[torch.Tensor],
+            emb: Optional[torch.Tensor], mode: int) -> torch.Tensor:
+    """raw (S,4) = (r,g,b,sigma).  p,d: (B,3) rays with z (B,N), or (S,3) samples with z None."""
+    dev = p.device
+    n_rays = p.shape[0]
+    n_samples = z.shape[1] if z is not None else 1
+    total = n_rays * n_samples
+    raw = torch.empty((total, 4), dtype=torch.float32, device=dev)
+    emb_rows = 0
+    if emb is not None:
+        emb_rows = emb.shape[0]
+    wbytes = int(lib().nerfw_mlp_workspace_bytes(n_rays, emb_rows))
+    ws_buf = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    ws = weights_struct(params)
+    with torch.cuda.device(dev):
+        check(lib().nerfw_mlp_fwd(C.byref(ws), _ptr(packed), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows,
+                                  n_rays, n_samples, int(mode), raw.data_ptr(), ws_buf.data_ptr(), wbytes, _stream()))
+    return raw
+
+
+def mlp_bwd(params: dict, grads: dict, p: torch.Tensor, d: torch.Tensor, z: Optional[torch.Tensor],
+            emb: Optional[torch.Tensor], d_raw: torch.Tensor, d_emb: Optional[torch.Tensor]) -> None:
+    """Accumulates into `grads` (same keys as params) and d_emb."""
+    dev = p.device
+    n_rays = p.shape[0]
+    n_samples = z.shape[1] if z is not None else 1
+    emb_rows = emb.shape[0] if emb is not None else 0
+    wbytes = int(lib().nerfw_mlp_bwd_workspace_bytes(n_rays, n_samples, emb_rows))
+    ws_buf = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    ws = weights_struct(params)
+    gs = weights_struct(grads)
+    with torch.cuda.device(dev):
+        check(lib().nerfw_mlp_bwd(C.byref(ws), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows, n_rays, n_samples,
+                                  d_raw.data_ptr(), C.byref(gs), _ptr(d_emb), ws_buf.data_ptr(), wbytes, _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ compositing
+def composite_fwd(raw: torch.Tensor, z: torch.Tensor, want_weights: bool = True):
+    b, n = z.shape
+    dev = z.device
+    rgb = torch.empty((b, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((b, 1), dtype=torch.float32, device=dev)
+    acc = torch.empty((b, 1), dtype=torch.float32, device=dev)
+    w = torch.empty((b, n), dtype=torch.float32, device=dev) if want_weights else None
+    with torch.cuda.device(dev):
+        check(lib().nerfw_composite_fwd(raw.data_ptr(), z.data_ptr(), b, n, rgb.data_ptr(), depth.data_ptr(),
+                                        acc.data_ptr(), _ptr(w), _stream()))
+    return rgb, depth, acc, w
+
+
+def composite_bwd(raw: torch.Tensor, z: torch.Tensor, d_rgb: torch.Tensor, d_depth: Optional[torch.Tensor],
+                  d_acc: Optional[torch.Tensor], d_w: Optional[torch.Tensor]) -> torch.Tensor:
+    b, n = z.shape
+    d_raw = torch.empty((b * n, 4), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        check(lib().nerfw_composite_bwd(raw.data_ptr(), z.data_ptr(), b, n, d_rgb.data_ptr(), _ptr(d_depth), _ptr(d_acc),
+                                        _ptr(d_w), d_raw.data_ptr(), _stream()))
+    return d_raw
+
+
+# ------------------------------------------------------------------------------------------------ training helpers
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+              lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0) -> None:
+    with torch.cuda.device(param.device):
+        check(lib().nerfw_adam(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                               param.numel(), lr, betas[0], betas[1], eps, int(step), grad_scale, _stream()))
+
+
+def mse(rgb: torch.Tensor, target: torch.Tensor, loss_scale: float = 1.0, want_grad: bool = True):
+    rgb = _f32c(rgb, "rgb")
+    target = _f32c(target, "target")
+    loss = torch.empty(1, dtype=torch.float32, device=rgb.device)
+    d = torch.empty_like(rgb) if want_grad else None
+    with torch.cuda.device(rgb.device):
+        check(lib().nerfw_mse(rgb.data_ptr(), target.data_ptr(), rgb.numel(), loss_scale, loss.data_ptr(), _ptr(d), _stream()))
+    return loss, d
+
+
+def quantize_u8(x: torch.Tensor) -> torch.Tensor:
+    x = _f32c(x, "x")
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().nerfw_quantize_u8(x.data_ptr(), x.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def selftest_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
+    """D = A B^T for A (128,K) bf16, B (N,K) bf16 through one tcgen05 tile (tests)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[0] == 128
+    a = a.contiguous()
+    b = b.contiguous()
+    d = torch.empty((128, b.shape[0]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().nerfw_selftest_umma(a.data_ptr(), b.data_ptr(), b.shape[0], a.shape[1], int(mode), d.data_ptr(), _stream()))
+    return d

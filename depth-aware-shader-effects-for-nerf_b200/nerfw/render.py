@@ -1,0 +1,79 @@
+"""volume_render with the reference's signature (src/render.py:5-97): sampling -> MLP -> compositing on sm_100a.
+
+Differences from the reference, all additive:
+  * `n_importance > 0` really runs the hierarchical fine pass (the reference's branch body is `pass`, F1); set
+    `fine_pass=False` (or NERFW_COARSE_ONLY=1) to reproduce the reference's coarse-only output exactly.
+  * extras gains 'acc' (sum of weights, F4) and, for the fine pass, the coarse outputs.
+  * `model` may be one NeRF (shared coarse/fine weights, F3) or a (coarse, fine) pair.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import ops
+from .autograd import RenderFn
+from .models import NeRF, resolve_mode
+
+
+def _shade(model: NeRF, o, d, z, emb, mode):
+    """(rgb (B,3), depth (B,1), acc (B,1), weights (B,N)) for given depths -- src/render.py:29-80."""
+    mode_id = resolve_mode(mode or model.mlp_mode)
+    names, tensors = model.kernel_params()
+    ops.require_device(o.device)
+    packed = model.packed_weights(names, tensors) if mode_id != 0 else None
+    if mode_id == 0:
+        ops.check_params({n: t.detach() for n, t in zip(names, tensors)})
+    needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or (emb is not None and emb.requires_grad))
+    if needs_grad:
+        return RenderFn.apply(mode_id, names, o, d, z, emb, packed, *tensors)
+    raw = ops.mlp_fwd({n: t.detach() for n, t in zip(names, tensors)}, packed, o, d, z,
+                      None if emb is None else emb.detach(), mode_id)
+    return ops.composite_fwd(raw, z, want_weights=True)
+
+
+def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
+                  appearance_embedding=None, background_color=None, perturb=True, *,
+                  mlp_dtype: Optional[str] = None, fine_pass: Optional[bool] = None, generator=None,
+                  t_rand=None, u_rand=None):
+    """Returns (rgb_map (...,3), depth_map (...,1), extras) like src/render.py:92-97.
+
+    `background_color` is accepted and ignored, as in the reference (src/render.py:6).  `t_rand` (B,N) / `u_rand`
+    (B,NI) inject the uniforms the reference draws at src/ray_utils.py:80 and :119 (otherwise torch.rand on the device,
+    in that order)."""
+    coarse, fine = (model if isinstance(model, (tuple, list)) else (model, model))
+    if fine_pass is None:
+        fine_pass = os.environ.get("NERFW_COARSE_ONLY", "0") != "1"
+    dev = coarse.rgb_linear.weight.device
+    if dev.type != "cuda":
+        raise RuntimeError(f"volume_render: the model is on {dev}; move it to a CUDA (sm_100) device -- there is no CPU path")
+    src_dev = rays_o.device
+    orig_shape = rays_o.shape
+    o = rays_o.to(dev, torch.float32).reshape(-1, 3).contiguous()
+    d = rays_d.to(dev, torch.float32).reshape(-1, 3).contiguous()
+    b = o.shape[0]
+    d = ops.normalize_dirs(d)                                              # src/render.py:19
+    emb = coarse._prep_emb(appearance_embedding, b, dev)                   # src/render.py:33-46
+    ztab = ops.depth_table(near, far, n_samples, dev)
+    tr = None
+    if perturb:
+        tr = t_rand.to(dev).reshape(b, n_samples) if t_rand is not None else torch.rand((b, n_samples), device=dev, generator=generator)
+    z, _ = ops.stratified(None, None, ztab, tr, b, want_pts=False)         # src/render.py:22 (pts never materialised)
+    rgb, depth, acc, w = _shade(coarse, o, d, z, emb, mlp_dtype)
+    extras = {}
+    if n_importance > 0 and fine_pass:
+        ur = u_rand.to(dev).reshape(b, n_importance) if u_rand is not None else torch.rand((b, n_importance), device=dev, generator=generator)
+        z_all = ops.sample_pdf(z, w.detach(), int(n_importance), ur)       # src/ray_utils.py:90-149
+        extras.update({"rgb_coarse": rgb.reshape(*orig_shape[:-1], 3), "depth_coarse": depth.reshape(*orig_shape[:-1], 1),
+                       "acc_coarse": acc, "weights_coarse": w.unsqueeze(-1), "z_vals_coarse": z})
+        z = z_all
+        rgb, depth, acc, w = _shade(fine, o, d, z, emb, mlp_dtype)
+    extras.update({"weights": w.unsqueeze(-1), "z_vals": z, "acc": acc})
+    rgb_map = rgb.reshape(*orig_shape[:-1], 3)
+    depth_map = depth.reshape(*orig_shape[:-1], 1)
+    if src_dev != dev:
+        rgb_map, depth_map = rgb_map.to(src_dev), depth_map.to(src_dev)
+        extras = {k: v.to(src_dev) for k, v in extras.items()}
+    return rgb_map, depth_map, extras

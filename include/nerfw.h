@@ -1,0 +1,184 @@
+/*
+ * nerfw.h -- C ABI of libnerfw_sm100.so, the B200 (sm_100a) NeRF-W ray-marching hot path.
+ *
+ * The reference (ByeongKyuPark/Depth-Aware-Shader-Effects-for-NeRF) has no FFI: its "plugin API" is the
+ * set of Python callables in src/ray_utils.py, src/render.py and src/models.py.  Each
+ * entry point below is what a ctypes binding for one of those callables would bind; the reference
+ * file:line it replaces is cited on every declaration.  INTEGRATION.md shows the Python-side stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types.
+ *  - every pointer is a DEVICE pointer unless its name ends in _host; all tensors are dense,
+ *    row-major fp32 (indices int64) and 16-byte aligned.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Functions only enqueue work;
+ *    they never synchronise, allocate or free device memory, and keep no pointer past the call.
+ *  - return value: 0 on success, a negative NERFW_E* code on failure; nerfw_last_error() then returns a
+ *    thread-local message.  There is no CPU fallback anywhere.
+ */
+#ifndef NERFW_H
+#define NERFW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERFW_ABI_VERSION 1
+
+enum {
+  NERFW_OK = 0,
+  NERFW_EINVAL = -1,   /* bad argument (shape, null pointer, unsupported architecture constant) */
+  NERFW_ECUDA = -2,    /* a CUDA runtime call or launch failed */
+  NERFW_EDEVICE = -3,  /* current device is not sm_100 */
+  NERFW_ESIZE = -4     /* workspace / packed buffer too small */
+};
+
+/* MLP arithmetic modes (nerfw_mlp_fwd `mode`). */
+enum {
+  NERFW_MLP_FP32 = 0,     /* CUDA-core fp32 FFMA; closest to the reference's fp32 nn.Linear */
+  NERFW_MLP_BF16X3 = 1,   /* tcgen05 kind::f16, operands split hi+lo bf16, 3 MMAs per product (~2^-16 rel) */
+  NERFW_MLP_BF16 = 2      /* tcgen05 kind::f16, single bf16 MMA (stated looser bounds) */
+};
+
+/* Architecture constants the kernels are specialised for (config.py:10-33 defaults). */
+#define NERFW_HIDDEN 256
+#define NERFW_LAYERS 8
+#define NERFW_SKIP 4
+#define NERFW_POS_LEVELS 10
+#define NERFW_DIR_LEVELS 4
+#define NERFW_POS_DIM 63   /* 3 + 3*2*10, src/models.py:22-27 */
+#define NERFW_DIR_DIM 27   /* 3 + 3*2*4 */
+#define NERFW_DIR_HIDDEN 128
+#define NERFW_APP_DIM 32
+
+/* The 24 state_dict tensors of src/models.py:80-103 in the reference layout ([out,in] row-major fp32).
+ * app_w/app_b may be NULL when use_appearance is False (src/models.py:99-101). */
+typedef struct NerfwWeights {
+  const float* pts_w[NERFW_LAYERS];  /* (256,63) (256,256)x3 (256,319) (256,256)x3 */
+  const float* pts_b[NERFW_LAYERS];  /* (256,) */
+  const float* density_w;            /* (1,256) */
+  const float* density_b;            /* (1,) */
+  const float* dir_w;                /* (128,283): cols 0-255 = h, 256-282 = enc_d (src/models.py:141) */
+  const float* dir_b;                /* (128,) */
+  const float* app_w;                /* (128,32) or NULL */
+  const float* app_b;                /* (128,) or NULL */
+  const float* rgb_w;                /* (3,128) */
+  const float* rgb_b;                /* (3,) */
+} NerfwWeights;
+
+/* Gradients, same layout; every pointer must be valid (app_* may be NULL iff the weights' are). */
+typedef struct NerfwGrads {
+  float* pts_w[NERFW_LAYERS];
+  float* pts_b[NERFW_LAYERS];
+  float* density_w;
+  float* density_b;
+  float* dir_w;
+  float* dir_b;
+  float* app_w;
+  float* app_b;
+  float* rgb_w;
+  float* rgb_b;
+} NerfwGrads;
+
+const char* nerfw_last_error(void);
+int nerfw_abi_version(void);
+/* 0 if the current CUDA device is compute capability 10.x, NERFW_EDEVICE otherwise. */
+int nerfw_check_device(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches counter). */
+uint64_t nerfw_launch_count(void);
+
+/* ---- rays: get_rays(height, width, focal_length, c2w)  -- src/ray_utils.py:4-50 ------------------------
+ * c2w_host: 12 floats, rows 0..2 of the camera-to-world matrix, row-major [r*4+c] (HOST memory).
+ * dirs (H,W,3) unit directions, bit-identical to the reference's CPU result; origins (H,W,3) may be NULL
+ * (the reference returns a stride-0 expand of c2w[:3,3], src/ray_utils.py:48). */
+int nerfw_raygen(int height, int width, float focal, const float* c2w_host, float* origins, float* dirs,
+                 void* stream);
+
+/* F.normalize(rays_d, dim=-1) -- src/render.py:19 (x / max(||x||, 1e-12)). in/out may alias. */
+int nerfw_normalize_dirs(const float* dirs, int64_t n_rays, float* out, void* stream);
+
+/* ---- sample_stratified(rays_o, rays_d, near, far, n_samples, perturb) -- src/ray_utils.py:52-88 --------
+ * ztab: the N-entry table near + linspace(0,1,N)*(far-near) (src/ray_utils.py:69-70), computed by the caller
+ * with host torch so its bits equal the reference's.  t_rand (B,N) uniforms or NULL (perturb=False).
+ * z (B,N) out; pts (B,N,3) out or NULL. */
+int nerfw_stratified(const float* rays_o, const float* rays_d, const float* ztab, const float* t_rand,
+                     int64_t n_rays, int n_samples, float* z, float* pts, void* stream);
+
+/* pts = o + d*z for given depths (src/ray_utils.py:86 and :147). */
+int nerfw_ray_points(const float* rays_o, const float* rays_d, const float* z, int64_t n_rays, int n_samples,
+                     float* pts, void* stream);
+
+/* ---- sample_importance(rays_o, rays_d, z_vals, weights, n_importance) -- src/ray_utils.py:90-149 -------
+ * (the "sample_pdf" of the north star; z-gather index clamped to N-1)
+ * u_lin: NI-entry table linspace(0,1,NI+1)[:-1] from host torch (:115); u_rand (B,NI) uniforms (:119).
+ * z_out (B,N+NI) sorted ascending.  Optional outputs (may be NULL): inds (B,NI) int64 = searchsorted result
+ * (:122), z_fine (B,NI) (:139), cdf (B,N+1) (:111-112). */
+int nerfw_sample_pdf(const float* z_vals, const float* weights, const float* u_lin, const float* u_rand,
+                     int64_t n_rays, int n_samples, int n_importance, float* z_out, int64_t* inds,
+                     float* z_fine, float* cdf, void* stream);
+
+/* ---- PositionalEncoding.__call__ -- src/models.py:14-46 ----------------------------------------------
+ * x (n,dim) -> out (n, dim*(include_input + 2*levels)): [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...]. */
+int nerfw_posenc(const float* x, int64_t n, int dim, int levels, int include_input, float* out, void* stream);
+
+/* ---- NeRF.forward(x, d, appearance_embedding) -- src/models.py:105-162 -------------------------------
+ * Packed weight cache for the tensor-core modes (derived data; the state_dict stays the source of truth). */
+size_t nerfw_packed_bytes(void);
+int nerfw_pack_weights(const NerfwWeights* w, void* packed, size_t packed_bytes, void* stream);
+
+/* Samples are given either per sample (pts (S,3), dirs (S,3); z == NULL, n_samples == 1, n_rays == S) or
+ * per ray (rays_o (B,3), unit rays_d (B,3), z (B,N)): sample (b,i) sits at o_b + d_b*z_bi with direction
+ * d_b (src/render.py:22-30), so pts is never materialised.
+ * emb: NULL, or (emb_rows, 32) with emb_rows == 1 (shared, src/train.py:68) or emb_rows == n_rays
+ * (per ray, src/render.py:39-44; per sample when z == NULL).
+ * out: raw (S,4) = (r,g,b,sigma) after sigmoid / relu (src/models.py:138,160).
+ * `packed` is required for the BF16X3/BF16 modes (else may be NULL); `workspace` must hold
+ * nerfw_mlp_workspace_bytes(n_rays, emb_rows) bytes. */
+size_t nerfw_mlp_workspace_bytes(int64_t n_rays, int64_t emb_rows);
+int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const float* pts_or_o, const float* dirs,
+                  const float* z, const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples, int mode,
+                  float* raw, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the above (autograd of src/models.py:105-162): d_raw (S,4) in; accumulates (+=) into grads and,
+ * if d_emb != NULL, into d_emb (emb_rows,32).  fp32 CUDA-core arithmetic. */
+size_t nerfw_mlp_bwd_workspace_bytes(int64_t n_rays, int n_samples, int64_t emb_rows);
+int nerfw_mlp_bwd(const NerfwWeights* w, const float* pts_or_o, const float* dirs, const float* z,
+                  const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples, const float* d_raw,
+                  const NerfwGrads* grads, float* d_emb, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- compositing: the tail of volume_render -- src/render.py:56-80 ------------------------------------
+ * raw (B,N,4) = (r,g,b,sigma), z (B,N).  Out: rgb_map (B,3), depth (B,1), acc (B,1) = sum of weights
+ * (SURVEY.md F4), weights (B,N) or NULL. */
+int nerfw_composite_fwd(const float* raw, const float* z, int64_t n_rays, int n_samples, float* rgb_map,
+                        float* depth, float* acc, float* weights, void* stream);
+/* autograd of the above: d_rgb_map (B,3), d_depth (B,1) or NULL, d_acc (B,1) or NULL, d_weights (B,N) or NULL
+ * -> d_raw (B,N,4) (overwritten). */
+int nerfw_composite_bwd(const float* raw, const float* z, int64_t n_rays, int n_samples, const float* d_rgb_map,
+                        const float* d_depth, const float* d_acc, const float* d_weights, float* d_raw,
+                        void* stream);
+
+/* ---- optimizer: torch.optim.Adam.step as used at src/train.py:33-39,92 (no weight decay, no amsgrad) ---
+ * One fused launch over a flat parameter buffer.  step is 1-based. grad_scale multiplies g first
+ * (1/world_size after the data-parallel all-reduce). */
+int nerfw_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+               float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+/* mse_loss(rgb, target) forward+backward in one launch (src/train.py:87): loss_out[0] = mean((a-b)^2),
+ * d_rgb = 2*(a-b)/n * loss_scale. */
+int nerfw_mse(const float* rgb, const float* target, int64_t n, float loss_scale, float* loss_out, float* d_rgb,
+              void* stream);
+
+/* rgb (n,3) float in [0,1] -> uint8, exactly (x*255).astype(uint8) of render_aligned_spiral.py:161-162;
+ * depth (n) -> uint8 by the min/max normalisation of :171-173 given dmin,dmax. */
+int nerfw_quantize_u8(const float* rgb, int64_t n_values, uint8_t* out, void* stream);
+
+/* Primitive self-test (tests only): D (128,n) fp32 = A (128,k) bf16 * B (n,k) bf16 ^T through one tcgen05 tile;
+ * mode 0 = A from shared memory, 1 = A from tensor memory.  Pins the descriptor / swizzle / TMEM layouts. */
+int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFW_H */

@@ -1,0 +1,157 @@
+"""K4/K5: the fused MLP forward (fp32 FFMA, bf16x3 and bf16 tcgen05 modes) and backward against the reference's
+NeRF.forward (golden) and the oracle / its autograd.  Tolerances are written next to each assertion."""
+import pytest
+import torch
+
+from gpu_util import maxabs, record
+
+pytestmark = pytest.mark.gpu
+
+# max-abs bounds on (rgb, sigma) of one MLP evaluation at random init (|sigma| ~ 0.1, rgb ~ 0.5)
+FWD_TOL = {"fp32": (2e-6, 2e-6), "bf16x3": (2e-5, 2e-5), "bf16": (8e-3, 8e-3)}
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,k", [(256, 64), (256, 256), (128, 128), (16, 64), (48, 192)])
+def test_umma_primitives(mode, n, k):
+    """One tcgen05 tile D = A B^T: pins the smem descriptor + 128B swizzle (mode 0) and the TMEM A layout (mode 1)."""
+    from nerfw import ops
+    g = torch.Generator().manual_seed(n + k + mode)
+    a = torch.randn(128, k, generator=g).bfloat16()
+    b = torch.randn(n, k, generator=g).bfloat16()
+    want = a.float() @ b.float().t()
+    got = ops.selftest_umma(a.cuda(), b.cuda(), mode)
+    err = maxabs(got, want)
+    record(f"umma_{'ts' if mode else 'ss'}_{n}x{k}", maxabs=err)
+    assert err <= 1e-3, err   # exact bf16 products, fp32 accumulation order only
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+def test_mlp_forward_golden(cuda_model, golden, mode):
+    model, emb = cuda_model
+    g = golden("mlp_64")
+    x, d = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["d"]).cuda()
+    model.mlp_mode = mode
+    try:
+        with torch.no_grad():
+            rgb, sigma = model(x, d, emb.unsqueeze(0))
+            rgb_n, sigma_n = model(x, d, None)
+    finally:
+        model.mlp_mode = None
+    assert rgb.shape == (64, 3) and sigma.shape == (64, 1)
+    e = dict(rgb=maxabs(rgb, g["rgb"]), sigma=maxabs(sigma, g["sigma"]), rgb_noemb=maxabs(rgb_n, g["rgb_noemb"]),
+             sigma_noemb=maxabs(sigma_n, g["sigma_noemb"]))
+    record(f"mlp_fwd_golden_{mode}", **e)
+    tr, ts = FWD_TOL[mode]
+    assert e["rgb"] <= tr and e["rgb_noemb"] <= tr and e["sigma"] <= ts and e["sigma_noemb"] <= ts, e
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+def test_mlp_forward_shapes_and_embeddings(cuda_model, oracle, state_dict, mode):
+    """ragged sizes (not multiples of the 64/128-sample tiles), (D,), (1,D) and per-sample (S,D) embeddings."""
+    model, emb = cuda_model
+    sd, _ = state_dict
+    gen = torch.Generator().manual_seed(77)
+    tr, ts = FWD_TOL[mode]
+    model.mlp_mode = mode
+    try:
+        for s in (1, 10, 63, 129, 1000):
+            x = (torch.rand(s, 3, generator=gen) - 0.5) * 8
+            d = torch.nn.functional.normalize(torch.randn(s, 3, generator=gen), dim=-1)
+            e_rows = torch.randn(s, 32, generator=gen)
+            for e in (None, e_rows[0], e_rows[:1], e_rows):
+                want_rgb, want_sigma = oracle.mlp_forward(sd, x, d, e)
+                with torch.no_grad():
+                    rgb, sigma = model(x.cuda(), d.cuda(), None if e is None else e.cuda())
+                assert maxabs(rgb, want_rgb) <= tr * 2 and maxabs(sigma, want_sigma) <= ts * 2, (s, None if e is None else e.shape)
+    finally:
+        model.mlp_mode = None
+
+
+def test_mlp_ray_form_equals_sample_form(cuda_model):
+    from nerfw import ops
+    model, emb = cuda_model
+    gen = torch.Generator().manual_seed(5)
+    b, n = 37, 64
+    o = torch.randn(b, 3, generator=gen).cuda()
+    d = torch.nn.functional.normalize(torch.randn(b, 3, generator=gen), dim=-1).cuda()
+    z = torch.sort(torch.rand(b, n, generator=gen) * 4 + 2, dim=-1).values.cuda()
+    pts = ops.ray_points(o, d, z).reshape(-1, 3)
+    dirs = d.unsqueeze(1).expand(-1, n, -1).reshape(-1, 3).contiguous()
+    e = emb.unsqueeze(0)
+    for mode in ("fp32", "bf16x3", "bf16"):
+        with torch.no_grad():
+            a = model.run_mlp(o, d, z, e, mode)
+            b_ = model.run_mlp(pts, dirs, None, e, mode)
+        assert torch.equal(a, b_), mode   # identical arithmetic, only the addressing differs
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("bf16", 1.5e-2)])
+def test_tensor_core_mlp_vs_fp32_kernel_large(cuda_model, mode, tol):
+    """200k samples (1563 tiles over 148 persistent CTAs): exercises the weight ring, phase wrap-around and tile loop."""
+    model, emb = cuda_model
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    b, n = 3125, 64
+    o = torch.randn(b, 3, device="cuda", generator=gen)
+    d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda", generator=gen), dim=-1)
+    z = torch.sort(torch.rand(b, n, device="cuda", generator=gen) * 4 + 2, dim=-1).values
+    e = emb.unsqueeze(0)
+    with torch.no_grad():
+        ref = model.run_mlp(o, d, z, e, "fp32")
+        got = model.run_mlp(o, d, z, e, mode)
+        again = model.run_mlp(o, d, z, e, mode)
+    err = maxabs(got, ref)
+    record(f"mlp_tc_vs_ffma_{mode}", maxabs=err)
+    assert err <= tol, err
+    assert torch.equal(got, again)   # deterministic
+
+
+def test_packed_cache_tracks_parameter_updates(cuda_model):
+    model, emb = cuda_model
+    x = torch.rand(130, 3, device="cuda")
+    d = torch.nn.functional.normalize(torch.randn(130, 3, device="cuda"), dim=-1)
+    with torch.no_grad():
+        a = model.run_mlp(x, d, None, None, "bf16x3")
+        saved = model.rgb_linear.bias.clone()
+        model.rgb_linear.bias.add_(1.0)          # bumps ._version -> the bf16 image must be rebuilt
+        b = model.run_mlp(x, d, None, None, "bf16x3")
+        model.rgb_linear.bias.copy_(saved)
+        c = model.run_mlp(x, d, None, None, "bf16x3")
+    assert float((b[:, :3] - a[:, :3]).min()) > 0.0
+    assert torch.equal(a, c)
+
+
+def test_mlp_backward_vs_oracle_autograd(cuda_model, oracle, state_dict):
+    """All 24 parameter gradients + the embedding gradient of sum(raw * cotangent), vs autograd through the oracle
+    in float64 on the same inputs.  Bound: 2e-4 of each tensor's max-abs gradient."""
+    model, emb = cuda_model
+    sd, _ = state_dict
+    gen = torch.Generator().manual_seed(21)
+    s = 200
+    x = (torch.rand(s, 3, generator=gen) - 0.5) * 6
+    d = torch.nn.functional.normalize(torch.randn(s, 3, generator=gen), dim=-1)
+    cot = torch.randn(s, 4, generator=gen)
+    for rows in (1, s):
+        e = torch.randn(rows, 32, generator=gen)
+        sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+        e64 = e.double().requires_grad_(True)
+        rgb, sigma = oracle.mlp_forward(sd64, x.double(), d.double(), e64)
+        (torch.cat([rgb, sigma], dim=-1) * cot.double()).sum().backward()
+        model.zero_grad()
+        eg = e.cuda().requires_grad_(True)
+        model.mlp_mode = "fp32"
+        try:
+            rgb_g, sigma_g = model(x.cuda(), d.cuda(), eg)
+        finally:
+            model.mlp_mode = None
+        (torch.cat([rgb_g, sigma_g], dim=-1) * cot.cuda()).sum().backward()
+        worst = 0.0
+        for k, p in model.named_parameters():
+            ref = sd64[k].grad
+            rel = maxabs(p.grad, ref) / (float(ref.abs().max()) + 1e-12)
+            worst = max(worst, rel)
+            assert rel <= 2e-4, (k, rel, rows)
+        rel_e = maxabs(eg.grad, e64.grad) / (float(e64.grad.abs().max()) + 1e-12)
+        record(f"mlp_bwd_rows{rows}", worst_param_rel=worst, emb_rel=rel_e)
+        assert rel_e <= 2e-4, rel_e
+    model.zero_grad()
