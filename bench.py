@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mlp-mode", default=os.environ.get("NERFW_MLP_MODE", "bf16x3"), choices=["bf16x3", "bf16", "fp32"])
-    ap.add_argument("--cpu-rays", type=int, default=int(os.environ.get("NERFW_CPU_SAMPLE_RAYS", "2048")),
+    ap.add_argument("--cpu-rays", type=int, default=int(os.environ.get("NERFW_CPU_SAMPLE_RAYS", "24000")),
                     help="rays in the bounded CPU sample (cpu_baseline / --impl reference step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

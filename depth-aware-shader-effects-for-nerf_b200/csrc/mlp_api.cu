@@ -26,8 +26,8 @@ extern "C" int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const fl
   int rc = check_weights(w, "nerfw_mlp_fwd");
   if (rc) return rc;
   NERFW_REQUIRE(n_rays >= 0 && n_samples >= 1, "nerfw_mlp_fwd: bad shape n_rays=%lld n_samples=%d", (long long)n_rays, n_samples);
-  NERFW_REQUIRE(z || n_samples == 1, "nerfw_mlp_fwd: n_samples must be 1 when z is NULL (per-sample inputs)");
   if (n_rays == 0) return NERFW_OK;
+  NERFW_REQUIRE(z || n_samples == 1, "nerfw_mlp_fwd: n_samples must be 1 when z is NULL (per-sample inputs)");
   NERFW_REQUIRE(pts_or_o && dirs && raw, "nerfw_mlp_fwd: null input/output pointer");
   NERFW_REQUIRE(aligned16(raw), "nerfw_mlp_fwd: raw must be 16-byte aligned");
   if (emb) {

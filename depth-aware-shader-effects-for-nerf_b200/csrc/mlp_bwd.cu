@@ -361,8 +361,8 @@ extern "C" int nerfw_mlp_bwd(const NerfwWeights* w, const float* pts_or_o, const
   NERFW_REQUIRE(grads->density_w && grads->density_b && grads->dir_w && grads->dir_b && grads->rgb_w && grads->rgb_b,
                 "nerfw_mlp_bwd: null head gradient");
   NERFW_REQUIRE(n_rays >= 0 && n_samples >= 1, "nerfw_mlp_bwd: bad shape");
-  NERFW_REQUIRE(z || n_samples == 1, "nerfw_mlp_bwd: n_samples must be 1 when z is NULL");
   if (n_rays == 0) return NERFW_OK;
+  NERFW_REQUIRE(z || n_samples == 1, "nerfw_mlp_bwd: n_samples must be 1 when z is NULL");
   NERFW_REQUIRE(pts_or_o && dirs && d_raw && workspace, "nerfw_mlp_bwd: null pointer");
   NERFW_REQUIRE(aligned16(d_raw) && aligned16(workspace), "nerfw_mlp_bwd: d_raw/workspace must be 16-byte aligned");
   if (emb) {

@@ -16,7 +16,7 @@ def make_inputs(b, n, seed, dense=False):
     return sigma, rgb, z
 
 
-@pytest.mark.parametrize("b,n,dense", [(1, 1, False), (5, 2, False), (300, 64, False), (300, 64, True), (64, 192, True),
+@pytest.mark.parametrize("b,n,dense", [(1, 2, False), (5, 2, False), (300, 64, False), (300, 64, True), (64, 192, True),
                                        (33, 100, False), (9, 768, False), (3, 1024, True)])
 def test_composite_forward(oracle, b, n, dense):
     from nerfw import ops
@@ -30,7 +30,7 @@ def test_composite_forward(oracle, b, n, dense):
     assert e["rgb"] <= 2e-5 and e["w"] <= 2e-6 and e["acc"] <= 2e-5 and e["depth"] <= 5e-5, e
 
 
-@pytest.mark.parametrize("b,n,dense", [(4, 1, False), (40, 64, False), (40, 64, True), (16, 192, False), (5, 768, False), (2, 1100, False)])
+@pytest.mark.parametrize("b,n,dense", [(4, 2, False), (40, 64, False), (40, 64, True), (16, 192, False), (5, 768, False), (2, 1100, False)])
 def test_composite_backward_vs_autograd(oracle, b, n, dense):
     from nerfw import ops
     sigma, rgb, z = make_inputs(b, n, 100 + b + n, dense)
@@ -59,6 +59,17 @@ def test_composite_backward_vs_autograd(oracle, b, n, dense):
     o_rgb2, _, _ = oracle.composite(s2, rgb.double(), z.double())
     (o_rgb2 * d_rgb.double()).sum().backward()
     assert maxabs(d_raw2[..., 3:], s2.grad) / (float(s2.grad.abs().max()) + 1e-12) <= 2e-4
+
+
+def test_single_sample_rays():
+    """N = 1 (the reference itself breaks there: its delta tensor comes out empty): w = 1 - exp(-sigma * 1e-3)."""
+    from nerfw import ops
+    raw = torch.tensor([[0.2, 0.4, 0.6, 50.0], [1.0, 1.0, 1.0, 0.0]], device="cuda")
+    z = torch.tensor([[3.0], [5.0]], device="cuda")
+    rgb, depth, acc, w = ops.composite_fwd(raw, z)
+    a = 1.0 - torch.exp(torch.tensor(-50.0 * 1e-3))
+    assert abs(float(w[0, 0]) - float(a)) <= 1e-7 and float(w[1, 0]) == 0.0
+    assert abs(float(depth[0, 0]) - 3.0) <= 1e-5 and float(depth[1, 0]) == 0.0
 
 
 def test_composite_full_size_properties():
