@@ -201,6 +201,35 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bench_train_step(nerfw, sd, dev, world, mode, n_rays=4096, steps=6, warmup=2):
+    """BASELINE.json configs[2]: 4096-ray batch per GPU, coarse+fine forward/backward + Adam, data parallel (one
+    all-reduce of the flat gradient buffer per step when world > 1).  Returns ms per step (max over ranks)."""
+    from config import Config
+    from nerfw.train import Trainer
+    m = nerfw.NeRF(Config())
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    table = torch.nn.Parameter(torch.randn(100, 32, device=dev))
+    tr = Trainer(m, table, lr=5e-4, mlp_dtype=mode)
+    g = torch.Generator(device=dev).manual_seed(7)
+    o = torch.tensor([0.0, 0.0, 4.0], device=dev).expand(n_rays, 3).contiguous()
+    d = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=dev, generator=g) * 0.3 + torch.tensor([0.0, 0.0, -1.0], device=dev), dim=-1)
+    tgt = torch.rand(n_rays, 3, device=dev, generator=g)
+    for _ in range(warmup):
+        tr.step(o, d, tgt, 3, NEAR, FAR, N_COARSE, N_IMPORTANCE, perturb=True, generator=g)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = tr.step(o, d, tgt, 3, NEAR, FAR, N_COARSE, N_IMPORTANCE, perturb=True, generator=g)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps, world)
+    return {"ms_per_step": ms, "rays_per_gpu": n_rays, "n_gpus": world, "samples": "64+128 (coarse+fine fwd/bwd) + Adam",
+            "forward_mode": mode, "backward": "fp32 CUDA-core MLP backward (recompute), composite_bwd",
+            "allreduce_bytes": int(tr.flat.grad.numel() * 4) if world > 1 else 0, "final_loss": float(loss)}
+
+
 def run_ours(args):
     import nerfw
     from config import Config
@@ -329,6 +358,26 @@ def run_ours(args):
                "sample_pdf": {"bound": "hbm", "achieved": rbytes / (rms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                               "unit": "GB/s", "frac": rbytes / (rms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": rms}}
 
+    # ---- secondary numbers: the other tensor-core mode, and the training step (BASELINE.json configs[2]) ------------
+    other_modes = {}
+    for m in ("bf16", "bf16x3"):
+        if m == mode:
+            continue
+        with torch.no_grad():
+            nerfw.volume_render(model, o_dev, d_dev, NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb_d,
+                                perturb=False, mlp_dtype=m, generator=gen)
+            barrier(world)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(2):
+                nerfw.volume_render(model, o_dev, d_dev, NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb_d,
+                                    perturb=False, mlp_dtype=m, generator=gen)
+            a1.record()
+            barrier(world)
+        ms = max_over_ranks(a0.elapsed_time(a1) / 2, world)
+        other_modes[m] = {"value": world * n_rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms}
+    train = bench_train_step(nerfw, sd, dev, world, mode)
+
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -367,6 +416,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof[mode],
         "roofline_other": {**{f"mlp_{k}": v for k, v in roof.items() if k != mode}, **hbm},
+        "other_modes": other_modes,
+        "train_step": train,
         "cpu_baseline": cpu,
         "parity_vs_oracle": parity,
     }
