@@ -429,6 +429,10 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # Exactly one JSON line may reach stdout: libraries (NCCL prints its version banner there) get stderr instead.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
