@@ -67,16 +67,18 @@ extern "C" int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const fl
   }
 }
 
-extern "C" size_t nerfw_packed_bytes(void) { return mlp_tc_packed_bytes(); }
+extern "C" size_t nerfw_packed_bytes(void) { return mlp_tc_packed_total_bytes(); }
 
 extern "C" int nerfw_pack_weights(const NerfwWeights* w, void* packed, size_t packed_bytes, void* stream) {
   int rc = check_weights(w, "nerfw_pack_weights");
   if (rc) return rc;
   NERFW_REQUIRE(packed, "nerfw_pack_weights: null destination");
-  if (packed_bytes < mlp_tc_packed_bytes()) {
-    set_error("nerfw_pack_weights: buffer of %zu bytes is smaller than nerfw_packed_bytes() = %zu", packed_bytes, mlp_tc_packed_bytes());
+  if (packed_bytes < mlp_tc_packed_total_bytes()) {
+    set_error("nerfw_pack_weights: buffer of %zu bytes is smaller than nerfw_packed_bytes() = %zu", packed_bytes, mlp_tc_packed_total_bytes());
     return NERFW_ESIZE;
   }
   NERFW_REQUIRE(aligned16(packed), "nerfw_pack_weights: destination must be 16-byte aligned");
-  return launch_pack_weights(*w, packed, as_stream(stream));
+  rc = launch_pack_weights(*w, packed, as_stream(stream));
+  if (rc) return rc;
+  return launch_pack_weights_t(*w, packed, as_stream(stream));
 }

@@ -4,7 +4,9 @@
 #include "mlp_common.cuh"
 
 namespace nerfw {
-size_t mlp_tc_packed_bytes();
+size_t mlp_tc_packed_bytes();          // forward image only
+size_t mlp_tc_packed_total_bytes();    // forward image + transposed (dgrad) image
+int launch_pack_weights_t(const NerfwWeights& w, void* packed, cudaStream_t stream);
 int launch_pack_weights(const NerfwWeights& w, void* packed, cudaStream_t stream);
 int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSource& src, const float* app_off,
                       int64_t n_total, bool x3, float* raw, cudaStream_t stream);

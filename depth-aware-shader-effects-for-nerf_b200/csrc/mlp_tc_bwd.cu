@@ -1,0 +1,926 @@
+// K5 (tensor-core mode): backward of the NeRF-W MLP (autograd of src/models.py:105-162) on tcgen05, bf16 operands with
+// fp32 accumulation.  Two kernels:
+//
+//  pass 1  `mlp_tc_bwd_pass1_kernel` -- per 128-sample tile, same warp-specialised skeleton as the forward kernel:
+//          forward recompute (activations X_l written to an HBM scratch tile as bf16, ReLU masks kept in shared
+//          memory), then the dgrad chain dZ_l = dH_{l+1} * relu', dH_l = dZ_l W_l with dZ as the TMEM A operand and the
+//          TRANSPOSED weight image as B; every dZ_l is written to the scratch tile as well.
+//  pass 2  `mlp_tc_wgrad_kernel` -- dW_l = dZ_l^T X_l as UMMA with both operands MN-major straight from the scratch
+//          tiles (they are stored as [sample][feature] blocks of 128 x 64 in the 128B-swizzled shared-memory image, so a
+//          tile is both a valid K-major forward operand and a valid MN-major wgrad operand); each CTA owns one weight
+//          block and a contiguous range of tiles, keeps the fp32 accumulator resident in TMEM for the whole range and
+//          flushes it once with atomics.  Bias / head gradients are column reductions of the same shared-memory tiles
+//          on CUDA cores while the MMAs run.
+//
+// Scratch tile = 71 blocks of 16 KB per 128 samples (1.16 MB): pass 2 is HBM-bound by construction (128 FLOP/B).
+#include "common.cuh"
+#include "mlp_common.cuh"
+#include "mlp_tc.cuh"
+#include "mlp_tc_layout.cuh"
+#include <string.h>
+
+namespace nerfw {
+namespace tcb {
+
+using namespace umma;
+using namespace tc;
+
+// ---- transposed weight image (dgrad B operands), consumption order: dir (2 chunks), L7..L1 (4 chunks each) ----------
+constexpr int NT_CHUNKS = 30;
+constexpr size_t WT_BYTES = (size_t)NT_CHUNKS * BIG_CHUNK;
+constexpr size_t PACKED_T_OFFSET = (PACKED_BYTES + 1023) & ~(size_t)1023;
+constexpr size_t PACKED_TOTAL = PACKED_T_OFFSET + WT_BYTES;
+
+// ---- scratch tile layout: 16 KB blocks [128 samples][64 features] bf16, 128B swizzle ------------------------------------
+constexpr uint32_t BLK = 16384;
+constexpr int XB_ENCX = 0;
+__host__ __device__ constexpr int XB_H(int l) { return 1 + 4 * (l - 1); }  // l = 1..8: output of trunk layer l-1
+constexpr int XB_ENCD = 33;
+constexpr int XB_HDT = 34;                                                   // relu(dir) + appearance feature, 2 blocks
+__host__ __device__ constexpr int ZB(int l) { return 36 + 4 * l; }         // l = 0..7: dZ of trunk layer l
+constexpr int ZB_DIR = 68;                                                   // 2 blocks
+constexpr int DLS_BLOCK = 70;                                                // 128 float4: (dlogit r,g,b, dsigma_pre)
+constexpr size_t TILE_BYTES = 71ull * BLK;
+
+// pass-1 shared memory: forward map, with the *_LO tiles reused for the ReLU masks and two small vectors appended
+constexpr uint32_t SM1_MASK_A = SM_PEX_LO;  // layers 0..3: [layer][row][ch][4 words]
+constexpr uint32_t SM1_MASK_B = SM_PED_LO;  // layers 4..7
+constexpr uint32_t SM1_DSIG = SM_RGB + 2 * TM * 16;  // rgb partial sums of BOTH column halves live at SM_RGB here
+constexpr uint32_t SM1_APPV = SM1_DSIG + TM * 4;
+constexpr uint32_t SM1_BAR = SM1_APPV + 128 * 4;
+constexpr uint32_t SM1_TMEMPTR = SM1_BAR + (2 * NSTAGES + 2) * 8;
+constexpr size_t SMEM1_BYTES = SM1_TMEMPTR + 16 + 1024;
+
+__global__ void __launch_bounds__(256) pack_weights_t_kernel(NerfwWeights w, uint8_t* __restrict__ packed_t) {
+  // one thread per (chunk, input feature n (row), 8-wide output group g)
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)NT_CHUNKS * 256 * 8) return;
+  int chunk = (int)(idx / (256 * 8));
+  int r = (int)(idx % (256 * 8));
+  int n = r / 8, g = r % 8;
+  const float* W;
+  int ld, ob;
+  if (chunk < 2) { W = w.dir_w; ld = 256 + NERFW_DIR_DIM; ob = chunk; }
+  else {
+    int l = 7 - (chunk - 2) / 4;
+    ob = (chunk - 2) % 4;
+    W = w.pts_w[l];
+    ld = (l == NERFW_SKIP) ? 256 + NERFW_POS_DIM : 256;
+  }
+  __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(__ldg(W + (size_t)(ob * 64 + g * 8 + e) * ld + n));
+  *reinterpret_cast<uint4*>(packed_t + (size_t)chunk * BIG_CHUNK + sw128_offset((uint32_t)n, (uint32_t)g * 8)) =
+      *reinterpret_cast<const uint4*>(v);
+}
+
+__device__ __forceinline__ uint32_t* mask_words(uint8_t* sm, int layer, uint32_t row, uint32_t ch) {
+  uint8_t* base = sm + (layer < 4 ? SM1_MASK_A : SM1_MASK_B);
+  return reinterpret_cast<uint32_t*>(base) + (((layer & 3) * TM + row) * 2 + ch) * 4;
+}
+
+// 32 consecutive features (16 packed bf16x2 words) of one sample row -> scratch block in the swizzled image
+__device__ __forceinline__ void store_row32(uint8_t* tile, int block0, uint32_t row, uint32_t col, const uint32_t (&p)[16]) {
+  uint8_t* blk = tile + (size_t)(block0 + (col >> 6)) * BLK;
+  const uint32_t k0 = col & 63;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 v = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+    *reinterpret_cast<uint4*>(blk + sw128_offset(row, k0 + 8 * c)) = v;
+  }
+}
+
+// ====================================================================================================================
+__global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint8_t* __restrict__ packed, SampleSource src,
+                                                                       const float4* __restrict__ app_off,
+                                                                       const float* __restrict__ app_vec,
+                                                                       const float4* __restrict__ d_raw, int64_t n_total,
+                                                                       uint8_t* __restrict__ scratch,
+                                                                       float* __restrict__ dl_acc) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + SM1_BAR);
+  uint64_t* empty = full + NSTAGES;
+  uint64_t* acc_full = empty + NSTAGES;
+  uint64_t* a_ready = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM1_TMEMPTR);
+  float* vec = reinterpret_cast<float*>(sm + SM_VEC);
+  float* sig_part = reinterpret_cast<float*>(sm + SM_SIG);
+  float4* rgb_part = reinterpret_cast<float4*>(sm + SM_RGB);  // [2][128]
+  float* dsig_s = reinterpret_cast<float*>(sm + SM1_DSIG);
+  float* appv = reinterpret_cast<float*>(sm + SM1_APPV);
+
+  if (warp == PRODUCER_WARP && lane == 0) {
+    for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(a_ready, EPI_THREADS);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc<512>(tmem_ptr);
+  if (warp < EPI_WARPS) {
+    const float* gv = reinterpret_cast<const float*>(packed + W_BYTES);
+    for (int i = tid; i < V_FLOATS; i += EPI_THREADS) vec[i] = __ldg(gv + i);
+    if (tid < 128) appv[tid] = app_vec ? __ldg(app_vec + tid) : 0.f;
+    // the unused half of the direction-encoding tile must be finite: it is a (discarded) wgrad operand column
+    for (int i = tid; i < 16384 / 16; i += EPI_THREADS) reinterpret_cast<uint4*>(sm + SM_PED_HI)[i] = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const int64_t ntiles = (n_total + TM - 1) / TM;
+  const uint8_t* packed_t = packed + PACKED_T_OFFSET;
+
+  if (warp == PRODUCER_WARP) {
+    if (lane == 0) {
+      Pipe p;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int i = 0; i < N_CHUNKS; ++i) {  // forward stream (hi copies only)
+          const uint32_t sz = i < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
+          mbar_wait(&empty[p.stage], p.phase ^ 1);
+          mbar_arrive_expect_tx(&full[p.stage], sz);
+          bulk_g2s(sm + SM_RING + p.stage * BIG_CHUNK, packed + chunk_offset(i), sz, &full[p.stage]);
+          p.advance();
+        }
+        for (int i = 0; i < NT_CHUNKS; ++i) {  // dgrad stream (transposed weights)
+          mbar_wait(&empty[p.stage], p.phase ^ 1);
+          mbar_arrive_expect_tx(&full[p.stage], BIG_CHUNK);
+          bulk_g2s(sm + SM_RING + p.stage * BIG_CHUNK, packed_t + (size_t)i * BIG_CHUNK, BIG_CHUNK, &full[p.stage]);
+          p.advance();
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      Pipe p;
+      uint32_t ar_phase = 0;
+      const uint32_t idesc256 = idesc_bf16(128, 256), idesc128 = idesc_bf16(128, 128);
+      const uint32_t ring = smem_u32(sm + SM_RING);
+      const uint32_t d_acc = tmem + COL_ACC;
+      auto kblock = [&](bool from_tmem, uint64_t a, uint32_t idesc, int ksteps, bool first) {
+        mbar_wait(&full[p.stage], p.phase);
+        tc_fence_after();
+        uint64_t b = smem_desc_sw128(ring + p.stage * BIG_CHUNK);
+        for (int k = 0; k < ksteps; ++k) {
+          uint32_t accf = (first && k == 0) ? 0u : 1u;
+          if (from_tmem) mma_ts(d_acc, (uint32_t)a + 8 * k, b + 2 * k, idesc, accf);
+          else mma_ss(d_acc, a + 2 * k, b + 2 * k, idesc, accf);
+        }
+        mma_commit(&empty[p.stage]);
+        p.advance();
+      };
+      const uint64_t pex = smem_desc_sw128(smem_u32(sm + SM_PEX_HI));
+      const uint64_t ped = smem_desc_sw128(smem_u32(sm + SM_PED_HI));
+      auto wait_a = [&]() {
+        mbar_wait(a_ready, ar_phase);
+        ar_phase ^= 1;
+        tc_fence_after();
+      };
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- forward recompute ----
+        for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
+          wait_a();
+          if (layer == 0) {
+            kblock(false, pex, idesc256, 4, true);
+          } else {
+            for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, idesc256, 4, kb == 0);
+            if (layer == NERFW_SKIP) kblock(false, pex, idesc256, 4, false);
+          }
+          mma_commit(acc_full);
+        }
+        wait_a();
+        for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, idesc128, 4, kb == 0);
+        kblock(false, ped, idesc128, 2, false);
+        mma_commit(acc_full);
+        // ---- dgrad chain: dH8 = dZdir W_dir[:, :256], then dH_l = dZ_l W_l[:, :256] for l = 7..1 ----
+        wait_a();
+        for (int kb = 0; kb < 2; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, idesc256, 4, kb == 0);
+        mma_commit(acc_full);
+        for (int l = NERFW_LAYERS - 1; l >= 1; --l) {
+          wait_a();
+          for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, idesc256, 4, kb == 0);
+          mma_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    const uint32_t quad = warp & 3, ch = warp >> 2;
+    const uint32_t row = quad * 32 + lane;
+    const uint32_t tlane = tmem + ((quad * 32) << 16);
+    uint32_t acc_phase = 0;
+    uint8_t* pex = sm + SM_PEX_HI;
+    uint8_t* ped = sm + SM_PED_HI;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t s = tile * TM + row;
+      const bool live = s < n_total;
+      uint8_t* tsc = scratch + (size_t)tile * TILE_BYTES;
+      // ---- encodings (as in the forward kernel) ----
+      {
+        float x[3] = {0.f, 0.f, 0.f};
+        if (live) src.position(s, x);
+        if (ch == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) put_enc<false>(pex, pex, row, c, x[c]);
+        } else {
+          put_enc<false>(pex, pex, row, 63, 0.f);
+        }
+        const int l0 = ch == 0 ? 0 : 7, l1 = ch == 0 ? 7 : NERFW_POS_LEVELS;
+        for (int l = l0; l < l1; ++l) {
+          float f = (float)(1u << l);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sn, cs;
+            sincosf(f * x[c], &sn, &cs);
+            put_enc<false>(pex, pex, row, 3 + 6 * l + c, sn);
+            put_enc<false>(pex, pex, row, 6 + 6 * l + c, cs);
+          }
+        }
+        if (ch == 1) {
+          float d[3] = {0.f, 0.f, 0.f};
+          if (live) src.direction(s, d);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) put_enc<false>(ped, ped, row, c, d[c]);
+          for (int l = 0; l < NERFW_DIR_LEVELS; ++l) {
+            float f = (float)(1u << l);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float sn, cs;
+              sincosf(f * d[c], &sn, &cs);
+              put_enc<false>(ped, ped, row, 3 + 6 * l + c, sn);
+              put_enc<false>(ped, ped, row, 6 + 6 * l + c, cs);
+            }
+          }
+          for (int k = NERFW_DIR_DIM; k < 32; ++k) put_enc<false>(ped, ped, row, k, 0.f);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(a_ready);
+      // encodings -> scratch (wgrad operands of layer 0, the skip part of layer 4 and the direction layer)
+      named_bar_sync(1, EPI_THREADS);
+      {
+        const int t = warp * 32 + lane;  // 0..255
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int o = (t + 256 * i) * 16;
+          *reinterpret_cast<uint4*>(tsc + (size_t)XB_ENCX * BLK + o) = *reinterpret_cast<const uint4*>(pex + o);
+          *reinterpret_cast<uint4*>(tsc + (size_t)XB_ENCD * BLK + o) = *reinterpret_cast<const uint4*>(ped + o);
+        }
+      }
+
+      // ---- forward trunk epilogues: next A operand, activation tile, ReLU mask ----
+      float sig = 0.f;
+      for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
+        mbar_wait(acc_full, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const float* bias = vec + V_PTSB + layer * 256;
+        uint32_t* mw = mask_words(sm, layer, row, ch);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t col = ch * 128 + q * 32;
+          uint32_t r[32];
+          tmem_ld32(tlane + COL_ACC + col, r);
+          tmem_wait_ld();
+          float v[32];
+          uint32_t bits = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = fmaxf(__uint_as_float(r[j]) + bias[col + j], 0.f);
+            bits |= (v[j] > 0.f ? 1u : 0u) << j;
+          }
+          mw[q] = bits;
+          if (layer == NERFW_LAYERS - 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sig = fmaf(v[j], vec[V_DENW + col + j], sig);
+          }
+          uint32_t ph[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          tmem_st16(tlane + COL_AHI + (col >> 1), ph);
+          store_row32(tsc, XB_H(layer + 1), row, col, ph);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+      }
+      sig_part[ch * TM + row] = sig;
+
+      // ---- direction layer epilogue: rgb, d logits, d sigma_pre, dZ of the direction layer ----
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      float p3[3] = {0.f, 0.f, 0.f};
+      uint32_t hmask[2];
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t col = ch * 64 + q * 32;
+        uint32_t r[32];
+        tmem_ld32(tlane + COL_ACC + col, r);
+        tmem_wait_ld();
+        uint32_t bits = 0;
+        uint32_t ph[16];
+        float hv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          hv[j] = fmaxf(__uint_as_float(r[j]) + vec[V_DIRB + col + j], 0.f);
+          bits |= (hv[j] > 0.f ? 1u : 0u) << j;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv[j], vec[V_RGBW + c * 128 + col + j], p3[c]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(hv[2 * j] + appv[col + 2 * j], hv[2 * j + 1] + appv[col + 2 * j + 1]);
+        store_row32(tsc, XB_HDT, row, col, ph);
+        hmask[q] = bits;
+      }
+      tc_fence_before();
+      rgb_part[ch * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
+      named_bar_sync(1, EPI_THREADS);
+      float dlog[3];
+      {
+        const float4 other = rgb_part[(ch ^ 1) * TM + row];
+        float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (app_off && live) off = __ldg(app_off);  // shared embedding only
+        float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) dr = __ldg(d_raw + s);
+        const float lg[3] = {p3[0] + other.x + vec[V_RGBB + 0] + off.x, p3[1] + other.y + vec[V_RGBB + 1] + off.y,
+                             p3[2] + other.z + vec[V_RGBB + 2] + off.z};
+        const float dd[3] = {dr.x, dr.y, dr.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float rgb = 1.0f / (1.0f + expf(-lg[c]));
+          dlog[c] = dd[c] * rgb * (1.0f - rgb);
+        }
+        const float pre = sig_part[row] + sig_part[TM + row] + vec[V_DENB];
+        const float ds = pre > 0.f ? dr.w : 0.f;
+        if (ch == 0) {
+          dsig_s[row] = ds;
+          *reinterpret_cast<float4*>(tsc + (size_t)DLS_BLOCK * BLK + row * 16) = make_float4(dlog[0], dlog[1], dlog[2], ds);
+          if (dl_acc) {  // sum of d logits per (shared) embedding row: appearance gradients are finished from it
+            float a0 = dlog[0], a1 = dlog[1], a2 = dlog[2];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+              a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+              a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            if (lane == 0) { atomicAdd(dl_acc + 0, a0); atomicAdd(dl_acc + 1, a1); atomicAdd(dl_acc + 2, a2); }
+          }
+        }
+      }
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t col = ch * 64 + q * 32;
+        uint32_t ph[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float g0 = dlog[0] * vec[V_RGBW + col + 2 * j] + dlog[1] * vec[V_RGBW + 128 + col + 2 * j] + dlog[2] * vec[V_RGBW + 256 + col + 2 * j];
+          float g1 = dlog[0] * vec[V_RGBW + col + 2 * j + 1] + dlog[1] * vec[V_RGBW + 128 + col + 2 * j + 1] + dlog[2] * vec[V_RGBW + 256 + col + 2 * j + 1];
+          if (!((hmask[q] >> (2 * j)) & 1u)) g0 = 0.f;
+          if (!((hmask[q] >> (2 * j + 1)) & 1u)) g1 = 0.f;
+          ph[j] = pack_bf16x2(g0, g1);
+        }
+        tmem_st16(tlane + COL_AHI + (col >> 1), ph);
+        store_row32(tsc, ZB_DIR, row, col, ph);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+      named_bar_sync(1, EPI_THREADS);  // dsig_s visible to the ch == 1 warps
+
+      // ---- dgrad epilogues, layer 7 down to 0: dZ_l = dH_{l+1} * [H_{l+1} > 0] ----
+      for (int l = NERFW_LAYERS - 1; l >= 0; --l) {
+        mbar_wait(acc_full, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const uint32_t* mw = mask_words(sm, l, row, ch);
+        const float ds = dsig_s[row];
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t col = ch * 128 + q * 32;
+          uint32_t r[32];
+          tmem_ld32(tlane + COL_ACC + col, r);
+          tmem_wait_ld();
+          const uint32_t bits = mw[q];
+          uint32_t ph[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float g0 = __uint_as_float(r[2 * j]), g1 = __uint_as_float(r[2 * j + 1]);
+            if (l == NERFW_LAYERS - 1) {  // + density head: d sigma_pre * w_sigma
+              g0 = fmaf(ds, vec[V_DENW + col + 2 * j], g0);
+              g1 = fmaf(ds, vec[V_DENW + col + 2 * j + 1], g1);
+            }
+            if (!((bits >> (2 * j)) & 1u)) g0 = 0.f;
+            if (!((bits >> (2 * j + 1)) & 1u)) g1 = 0.f;
+            ph[j] = pack_bf16x2(g0, g1);
+          }
+          if (l > 0) tmem_st16(tlane + COL_AHI + (col >> 1), ph);
+          store_row32(tsc, ZB(l), row, col, ph);
+        }
+        if (l > 0) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(a_ready);
+        } else {
+          tc_fence_before();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ====================================================================================================================
+// pass 2: weight gradients
+struct WgradBlock {
+  int dz_block;     // first dZ block in the scratch tile
+  int n_mhalves;    // outputs / 128 (1 or 2)
+  int x_block;      // first X block (-1: no MMA, rgb-head reduction only)
+  int x_nblocks;    // input features / 64
+  int n_valid;      // valid input features (<= 64 * x_nblocks)
+  int ld;           // row pitch of the destination weight matrix
+  int k0;           // first destination column
+  int flags;        // 1: bias column sums, 2: density head (needs dls + X = H8), 4: rgb head block
+  float* dW;        // [outputs][ld]
+  float* db;        // [outputs] or null
+};
+constexpr int MAX_UNITS = 148;
+struct WgradPlan {
+  int n_units;
+  int unit_block[MAX_UNITS];
+  int unit_t0[MAX_UNITS];
+  int unit_t1[MAX_UNITS];
+  WgradBlock blocks[13];
+  float* d_density_w;
+  float* d_density_b;
+  float* d_rgb_w;
+  float* d_rgb_b;
+};
+
+constexpr int W2_THREADS = 192;          // warp 0 producer, warp 1 MMA, warps 2..5 reducers / flush
+constexpr int W2_STAGES = 3;
+constexpr uint32_t W2_PIECE = 8192;      // 64 samples x 64 features
+constexpr uint32_t W2_DZ = 0;            // up to 4 pieces
+constexpr uint32_t W2_X = 4 * W2_PIECE;  // up to 4 pieces
+constexpr uint32_t W2_DLS = 8 * W2_PIECE;            // 64 float4
+constexpr uint32_t W2_STAGE = 8 * W2_PIECE + 2048;   // 67 584 B, 1024-aligned
+constexpr uint32_t W2_BAR = W2_STAGES * W2_STAGE;
+constexpr size_t SMEM2_BYTES = W2_BAR + 128 + 1024;
+
+// MN-major operand tile: rows = K (samples), 64 features (128 B) per row, 8-row groups 1024 B apart (SBO), consecutive
+// 64-feature blocks `lbo` bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __host__ constexpr uint32_t idesc_bf16_mn(uint32_t M, uint32_t N) { return idesc_bf16(M, N) | (1u << 15) | (1u << 16); }
+
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+
+__global__ void __launch_bounds__(W2_THREADS, 1) mlp_tc_wgrad_kernel(const __grid_constant__ WgradPlan plan,
+                                                                     const uint8_t* __restrict__ scratch) {
+  if ((int)blockIdx.x >= plan.n_units) return;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + W2_BAR);
+  uint64_t* empty = full + W2_STAGES;
+  uint64_t* done = empty + W2_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  const WgradBlock& wb = plan.blocks[plan.unit_block[blockIdx.x]];
+  const int t0 = plan.unit_t0[blockIdx.x], t1 = plan.unit_t1[blockIdx.x];
+  const bool has_mma = wb.x_block >= 0 && !(wb.flags & 4);
+  const int n_dz = 2 * wb.n_mhalves;
+  const int N = 64 * wb.x_nblocks;
+  const bool need_dls = (wb.flags & 6) != 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < W2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 128); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const int n_stages_total = (t1 - t0) * 2;  // two 64-sample halves per tile
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_stages_total; ++it) {
+        const int tile = t0 + (it >> 1), half = it & 1;
+        const uint8_t* tsc = scratch + (size_t)tile * TILE_BYTES + (size_t)half * W2_PIECE;
+        uint8_t* st = sm + stage * W2_STAGE;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint32_t bytes = (uint32_t)(n_dz + wb.x_nblocks) * W2_PIECE + (need_dls ? 1024u : 0u);
+        mbar_arrive_expect_tx(&full[stage], bytes);
+        for (int j = 0; j < n_dz; ++j) bulk_g2s(st + W2_DZ + j * W2_PIECE, tsc + (size_t)(wb.dz_block + j) * BLK, W2_PIECE, &full[stage]);
+        const int xb = wb.x_block >= 0 ? wb.x_block : 0;
+        for (int j = 0; j < wb.x_nblocks; ++j) bulk_g2s(st + W2_X + j * W2_PIECE, tsc + (size_t)(xb + j) * BLK, W2_PIECE, &full[stage]);
+        if (need_dls)
+          bulk_g2s(st + W2_DLS, scratch + (size_t)tile * TILE_BYTES + (size_t)DLS_BLOCK * BLK + (size_t)half * 1024, 1024, &full[stage]);
+        if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = idesc_bf16_mn(128, (uint32_t)N);
+      for (int it = 0; it < n_stages_total; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (has_mma) {
+          const uint32_t st = smem_u32(sm + stage * W2_STAGE);
+          const uint64_t b = smem_desc_sw128_mn(st + W2_X, W2_PIECE);
+          for (int h = 0; h < wb.n_mhalves; ++h) {
+            const uint64_t a = smem_desc_sw128_mn(st + W2_DZ + (uint32_t)h * 2 * W2_PIECE, W2_PIECE);
+            for (int ks = 0; ks < 4; ++ks)  // 64 samples = 4 K steps of 16 rows (2 KB each)
+              mma_ss(tmem + (uint32_t)(h * N), a + 128 * ks, b + 128 * ks, idesc, (it | ks) ? 1u : 0u);
+          }
+          mma_commit(&empty[stage]);
+        } else {
+          mbar_arrive(&empty[stage]);
+        }
+        if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (has_mma) mma_commit(done); else mbar_arrive(done);
+    }
+  } else {
+    // ---- reducers: bias column sums / head gradients from the shared-memory tiles, then the accumulator flush ----
+    const int rt = tid - 64;  // 0..127
+    float bsum[2] = {0.f, 0.f};             // bias: output columns 2 rt, 2 rt + 1
+    float dsw[2] = {0.f, 0.f};              // density head: input columns 2 rt, 2 rt + 1
+    float rg[3] = {0.f, 0.f, 0.f};          // rgb head: column rt, three channels
+    float hb[4] = {0.f, 0.f, 0.f, 0.f};     // rgb / density bias partial sums (threads 0..2 / thread 0)
+    int stage = 0;
+    uint32_t phase = 0;
+    const int c2 = 2 * rt;
+    for (int it = 0; it < n_stages_total; ++it) {
+      mbar_wait(&full[stage], phase);
+      const uint8_t* st = sm + stage * W2_STAGE;
+      const float4* dls = reinterpret_cast<const float4*>(st + W2_DLS);
+      if ((wb.flags & 1) && c2 < 128 * wb.n_mhalves) {
+        const uint8_t* piece = st + W2_DZ + (c2 >> 6) * W2_PIECE;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+          uint32_t v = *reinterpret_cast<const uint32_t*>(piece + sw128_offset((uint32_t)r, (uint32_t)(c2 & 63)));
+          float2 f = bf16x2_to_float2(v);
+          a0 += f.x; a1 += f.y;
+        }
+        bsum[0] += a0; bsum[1] += a1;
+      }
+      if (wb.flags & 2) {
+        // d density_w[k] += sum_s dsig[s] * h8[s][k]; thread rt owns input columns 2 rt, 2 rt + 1
+        const uint8_t* piece = st + W2_X + (c2 >> 6) * W2_PIECE;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+          uint32_t v = *reinterpret_cast<const uint32_t*>(piece + sw128_offset((uint32_t)r, (uint32_t)(c2 & 63)));
+          float2 f = bf16x2_to_float2(v);
+          float ds = dls[r].w;
+          a0 = fmaf(ds, f.x, a0); a1 = fmaf(ds, f.y, a1);
+        }
+        dsw[0] += a0; dsw[1] += a1;
+        if (rt == 0) {
+          float a = 0.f;
+          for (int r = 0; r < 64; ++r) a += dls[r].w;
+          hb[3] += a;
+        }
+      }
+      if (wb.flags & 4) {
+        // d rgb_w[c][k] += sum_s dlog[s][c] * hdt[s][k]; thread rt owns input column rt (128 columns = 2 pieces)
+        const uint8_t* piece = st + W2_X + (rt >> 6) * W2_PIECE;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+          float h = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(piece + sw128_offset((uint32_t)r, (uint32_t)(rt & 63))));
+          float4 d = dls[r];
+          a0 = fmaf(d.x, h, a0); a1 = fmaf(d.y, h, a1); a2 = fmaf(d.z, h, a2);
+        }
+        rg[0] += a0; rg[1] += a1; rg[2] += a2;
+        if (rt < 3) {
+          float a = 0.f;
+          for (int r = 0; r < 64; ++r) {
+            float4 d = dls[r];
+            a += rt == 0 ? d.x : (rt == 1 ? d.y : d.z);
+          }
+          hb[rt] += a;
+        }
+      }
+      mbar_arrive(&empty[stage]);
+      if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ---- flush ----
+    if ((wb.flags & 1) && c2 < 128 * wb.n_mhalves) {
+      atomicAdd(wb.db + c2, bsum[0]);
+      atomicAdd(wb.db + c2 + 1, bsum[1]);
+    }
+    if (wb.flags & 2) {
+      atomicAdd(plan.d_density_w + 2 * rt, dsw[0]);
+      atomicAdd(plan.d_density_w + 2 * rt + 1, dsw[1]);
+      if (rt == 0) atomicAdd(plan.d_density_b, hb[3]);
+    }
+    if (wb.flags & 4) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) atomicAdd(plan.d_rgb_w + c * 128 + rt, rg[c]);
+      if (rt < 3) atomicAdd(plan.d_rgb_b + rt, hb[rt]);
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (has_mma && n_stages_total > 0) {
+      const uint32_t quad = warp & 3;
+      const uint32_t tl = tmem + ((quad * 32) << 16);
+      for (int h = 0; h < wb.n_mhalves; ++h) {
+        const int o = h * 128 + quad * 32 + lane;
+        float* dst = wb.dW + (size_t)o * wb.ld + wb.k0;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tl + (uint32_t)(h * N + c0), r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < wb.n_valid) atomicAdd(dst + c0 + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// appearance branch, shared embedding: G = W_rgb^T DL; dW_rgb[c][k] += DL[c] a[k] (a = W_app e + b_app);
+// dW_app[k][q] += G[k] e[q]; db_app[k] += G[k]; d_emb[q] += sum_k G[k] W_app[k][q]
+__global__ void __launch_bounds__(128) app_bwd_shared_kernel(NerfwWeights w, NerfwGrads g, const float* __restrict__ emb,
+                                                             const float* __restrict__ app_vec,
+                                                             const float* __restrict__ dl, float* __restrict__ d_emb) {
+  __shared__ float gk[NERFW_DIR_HIDDEN];
+  const int k = threadIdx.x;
+  const float d0 = dl[0], d1 = dl[1], d2 = dl[2];
+  const float G = d0 * __ldg(w.rgb_w + k) + d1 * __ldg(w.rgb_w + 128 + k) + d2 * __ldg(w.rgb_w + 256 + k);
+  gk[k] = G;
+  const float a = app_vec[k];
+  atomicAdd(g.rgb_w + k, d0 * a);
+  atomicAdd(g.rgb_w + 128 + k, d1 * a);
+  atomicAdd(g.rgb_w + 256 + k, d2 * a);
+  for (int q = 0; q < NERFW_APP_DIM; ++q) atomicAdd(g.app_w + k * NERFW_APP_DIM + q, G * __ldg(emb + q));
+  atomicAdd(g.app_b + k, G);
+  __syncthreads();
+  if (d_emb && k < NERFW_APP_DIM) {
+    float de = 0.f;
+    for (int kk = 0; kk < NERFW_DIR_HIDDEN; ++kk) de = fmaf(gk[kk], __ldg(w.app_w + kk * NERFW_APP_DIM + k), de);
+    atomicAdd(d_emb + k, de);
+  }
+}
+
+// a[k] = W_app e + b_app (128 floats) for the shared embedding
+__global__ void __launch_bounds__(128) app_vec_kernel(NerfwWeights w, const float* __restrict__ emb, float* __restrict__ out) {
+  const int k = threadIdx.x;
+  float a = __ldg(w.app_b + k);
+#pragma unroll 8
+  for (int q = 0; q < NERFW_APP_DIM; ++q) a = fmaf(__ldg(w.app_w + k * NERFW_APP_DIM + q), __ldg(emb + q), a);
+  out[k] = a;
+}
+
+// MN-major self-test: D (128 x N) = At^T Bt with At (K x 128) and Bt (K x N) row-major bf16 (K, N multiples of 64)
+__global__ void __launch_bounds__(128, 1) umma_selftest_mn_kernel(const __nv_bfloat16* __restrict__ At,
+                                                                  const __nv_bfloat16* __restrict__ Bt, int N, int K,
+                                                                  float* __restrict__ D) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  uint8_t* sA = sm;            // 2 blocks of K rows x 128 B
+  uint8_t* sB = sm + 65536;    // N/64 blocks of K rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 65536 + 131072);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t blk = (uint32_t)K * 128u;
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  for (int idx = tid; idx < K * 128; idx += 128) {
+    int k = idx / 128, m = idx % 128;
+    *reinterpret_cast<__nv_bfloat16*>(sA + (m / 64) * blk + sw128_offset(k, m % 64)) = At[idx];
+  }
+  for (int idx = tid; idx < K * N; idx += 128) {
+    int k = idx / N, n = idx % N;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (n / 64) * blk + sw128_offset(k, n % 64)) = Bt[idx];
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16_mn(128, (uint32_t)N);
+    const uint64_t a = smem_desc_sw128_mn(smem_u32(sA), blk);
+    const uint64_t b = smem_desc_sw128_mn(smem_u32(sB), blk);
+    for (int ks = 0; ks < K / 16; ++ks) mma_ss(tmem, a + 128 * ks, b + 128 * ks, idesc, ks ? 1u : 0u);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  {
+    const uint32_t tl = tmem + ((warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tl + c0, r);
+      tmem_wait_ld();
+      for (int j = 0; j < 32; ++j) D[(size_t)tid * N + c0 + j] = __uint_as_float(r[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace tcb
+
+size_t mlp_tc_packed_total_bytes() { return tcb::PACKED_TOTAL; }
+
+int launch_pack_weights_t(const NerfwWeights& w, void* packed, cudaStream_t stream) {
+  const int64_t total = (int64_t)tcb::NT_CHUNKS * 256 * 8;
+  tcb::pack_weights_t_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(
+      w, reinterpret_cast<uint8_t*>(packed) + tcb::PACKED_T_OFFSET);
+  NERFW_LAUNCHED();
+  return NERFW_OK;
+}
+
+}  // namespace nerfw
+
+using namespace nerfw;
+
+extern "C" size_t nerfw_mlp_bwd_tc_workspace_bytes(int64_t n_rays, int n_samples) {
+  const int64_t total = n_rays * (int64_t)(n_samples > 0 ? n_samples : 1);
+  const int64_t ntiles = ceil_div64(total, tc::TM);
+  return 4096 + (size_t)ntiles * tcb::TILE_BYTES;
+}
+
+// Same contract as nerfw_mlp_bwd (include/nerfw.h), tensor-core arithmetic; shared (emb_rows == 1) or no embedding only.
+extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const float* pts_or_o, const float* dirs,
+                                const float* z, const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples,
+                                const float* d_raw, const NerfwGrads* grads, float* d_emb, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  NERFW_REQUIRE(w && grads && packed, "nerfw_mlp_bwd_tc: null weights, grads or packed weights");
+  for (int i = 0; i < NERFW_LAYERS; ++i)
+    NERFW_REQUIRE(w->pts_w[i] && w->pts_b[i] && grads->pts_w[i] && grads->pts_b[i], "nerfw_mlp_bwd_tc: null pts_linears.%d parameter or gradient", i);
+  NERFW_REQUIRE(grads->density_w && grads->density_b && grads->dir_w && grads->dir_b && grads->rgb_w && grads->rgb_b,
+                "nerfw_mlp_bwd_tc: null head gradient");
+  NERFW_REQUIRE(n_rays >= 0 && n_samples >= 1, "nerfw_mlp_bwd_tc: bad shape");
+  if (n_rays == 0) return NERFW_OK;
+  NERFW_REQUIRE(z || n_samples == 1, "nerfw_mlp_bwd_tc: n_samples must be 1 when z is NULL");
+  NERFW_REQUIRE(pts_or_o && dirs && d_raw && workspace, "nerfw_mlp_bwd_tc: null pointer");
+  NERFW_REQUIRE(aligned16(d_raw) && aligned16(workspace), "nerfw_mlp_bwd_tc: d_raw and workspace must be 16-byte aligned");
+  if (emb) {
+    NERFW_REQUIRE(emb_rows == 1, "nerfw_mlp_bwd_tc: only a shared embedding (emb_rows == 1) is supported; use nerfw_mlp_bwd for per-ray embeddings");
+    NERFW_REQUIRE(w->app_w && w->app_b && grads->app_w && grads->app_b, "nerfw_mlp_bwd_tc: embedding given but appearance parameters/gradients are null");
+  }
+  const size_t need = nerfw_mlp_bwd_tc_workspace_bytes(n_rays, z ? n_samples : 1);
+  if (workspace_bytes < need) {
+    set_error("nerfw_mlp_bwd_tc: workspace of %zu bytes, need %zu", workspace_bytes, need);
+    return NERFW_ESIZE;
+  }
+  cudaStream_t st = as_stream(stream);
+  // header: [app_off float4][dl_acc 4 floats][app_vec 128 floats] ... tiles from +4096
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  float* app_off = reinterpret_cast<float*>(base);
+  float* dl_acc = reinterpret_cast<float*>(base + 16);
+  float* app_vec = reinterpret_cast<float*>(base + 64);
+  uint8_t* scratch = base + 4096;
+  NERFW_CUDA(cudaMemsetAsync(base, 0, 4096, st));
+  if (emb) {
+    int rc = launch_app_offset(*w, emb, 1, app_off, st);
+    if (rc) return rc;
+    tcb::app_vec_kernel<<<1, 128, 0, st>>>(*w, emb, app_vec);
+    NERFW_LAUNCHED();
+  }
+  SampleSource src;
+  src.p = pts_or_o;
+  src.d = dirs;
+  src.z = z;
+  src.emb = emb;
+  src.n_per_ray = z ? n_samples : 1;
+  src.emb_shared = 1;
+  const int64_t total = n_rays * (z ? n_samples : 1);
+  const int64_t ntiles = ceil_div64(total, tc::TM);
+  NERFW_REQUIRE(ntiles < (1ll << 30), "nerfw_mlp_bwd_tc: too many samples");
+
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    NERFW_CUDA(cudaFuncSetAttribute(tcb::mlp_tc_bwd_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::SMEM1_BYTES));
+    NERFW_CUDA(cudaFuncSetAttribute(tcb::mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::SMEM2_BYTES));
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  int64_t grid1 = ntiles < sms ? ntiles : sms;
+  tcb::mlp_tc_bwd_pass1_kernel<<<(unsigned)grid1, tc::THREADS, tcb::SMEM1_BYTES, st>>>(
+      reinterpret_cast<const uint8_t*>(packed), src, emb ? reinterpret_cast<const float4*>(app_off) : nullptr,
+      emb ? app_vec : nullptr, reinterpret_cast<const float4*>(d_raw), total, scratch, emb ? dl_acc : nullptr);
+  NERFW_LAUNCHED();
+
+  // ---- pass-2 plan: one weight block and one contiguous tile range per CTA, CTAs shared out by bytes per tile ----
+  tcb::WgradPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  int nb = 0;
+  auto add = [&](int dzb, int mh, int xb, int xn, int nvalid, int ld, int k0, int flags, float* dW, float* db) {
+    tcb::WgradBlock& b = plan.blocks[nb++];
+    b.dz_block = dzb; b.n_mhalves = mh; b.x_block = xb; b.x_nblocks = xn; b.n_valid = nvalid; b.ld = ld; b.k0 = k0;
+    b.flags = flags; b.dW = dW; b.db = db;
+  };
+  add(tcb::ZB(0), 2, tcb::XB_ENCX, 1, NERFW_POS_DIM, NERFW_POS_DIM, 0, 1, grads->pts_w[0], grads->pts_b[0]);
+  for (int l = 1; l < NERFW_LAYERS; ++l) {
+    const int ld = (l == NERFW_SKIP) ? 256 + NERFW_POS_DIM : 256;
+    add(tcb::ZB(l), 2, tcb::XB_H(l), 4, 256, ld, 0, 1, grads->pts_w[l], grads->pts_b[l]);
+    if (l == NERFW_SKIP) add(tcb::ZB(l), 2, tcb::XB_ENCX, 1, NERFW_POS_DIM, ld, 256, 0, grads->pts_w[l], nullptr);
+  }
+  add(tcb::ZB_DIR, 1, tcb::XB_H(8), 4, 256, 256 + NERFW_DIR_DIM, 0, 1 | 2, grads->dir_w, grads->dir_b);
+  add(tcb::ZB_DIR, 1, tcb::XB_ENCD, 1, NERFW_DIR_DIM, 256 + NERFW_DIR_DIM, 256, 0, grads->dir_w, nullptr);
+  add(tcb::ZB_DIR, 0, tcb::XB_HDT, 2, 128, 128, 0, 4, grads->rgb_w, grads->rgb_b);
+  plan.d_density_w = grads->density_w;
+  plan.d_density_b = grads->density_b;
+  plan.d_rgb_w = grads->rgb_w;
+  plan.d_rgb_b = grads->rgb_b;
+  double cost[13], csum = 0;
+  for (int b = 0; b < nb; ++b) {
+    const tcb::WgradBlock& wb = plan.blocks[b];
+    cost[b] = 2.0 * wb.n_mhalves + wb.x_nblocks + 0.25;
+    csum += cost[b];
+  }
+  const int max_units = sms < tcb::MAX_UNITS ? sms : tcb::MAX_UNITS;
+  int alloc[13], used = 0;
+  for (int b = 0; b < nb; ++b) {
+    int c = (int)(cost[b] / csum * max_units);
+    if (c < 1) c = 1;
+    if (c > ntiles) c = (int)ntiles;
+    alloc[b] = c;
+    used += c;
+  }
+  while (used > max_units) {  // trim the largest allocations
+    int bi = 0;
+    for (int b = 1; b < nb; ++b) if (alloc[b] > alloc[bi]) bi = b;
+    if (alloc[bi] <= 1) break;
+    --alloc[bi]; --used;
+  }
+  for (bool grew = true; grew && used < max_units;) {  // hand out the remainder to the most loaded blocks
+    grew = false;
+    int bi = -1;
+    double worst = 0;
+    for (int b = 0; b < nb; ++b) {
+      if (alloc[b] >= ntiles) continue;
+      double load = cost[b] / alloc[b];
+      if (load > worst) { worst = load; bi = b; }
+    }
+    if (bi >= 0) { ++alloc[bi]; ++used; grew = true; }
+  }
+  int u = 0;
+  for (int b = 0; b < nb; ++b) {
+    for (int c = 0; c < alloc[b]; ++c) {
+      int64_t t0 = ntiles * c / alloc[b], t1 = ntiles * (c + 1) / alloc[b];
+      if (t1 <= t0) continue;
+      plan.unit_block[u] = b;
+      plan.unit_t0[u] = (int)t0;
+      plan.unit_t1[u] = (int)t1;
+      ++u;
+    }
+  }
+  plan.n_units = u;
+  tcb::mlp_tc_wgrad_kernel<<<(unsigned)u, tcb::W2_THREADS, tcb::SMEM2_BYTES, st>>>(plan, scratch);
+  NERFW_LAUNCHED();
+  if (emb) {
+    tcb::app_bwd_shared_kernel<<<1, 128, 0, st>>>(*w, *grads, emb, app_vec, dl_acc, d_emb);
+    NERFW_LAUNCHED();
+  }
+  return NERFW_OK;
+}
+
+// MN-major primitive self-test: D (128,n) fp32 = At^T Bt, At (k,128), Bt (k,n) bf16 row-major.
+extern "C" int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, int n, int k, float* d, void* stream) {
+  NERFW_REQUIRE(at_bf16 && bt_bf16 && d, "nerfw_selftest_umma_mn: null pointer");
+  NERFW_REQUIRE(n >= 64 && n <= 256 && n % 64 == 0, "nerfw_selftest_umma_mn: N must be a multiple of 64 in [64,256]");
+  NERFW_REQUIRE(k >= 16 && k <= 256 && k % 16 == 0, "nerfw_selftest_umma_mn: K must be a multiple of 16 in [16,256]");
+  const size_t smem = 65536 + 131072 + 64 + 1024;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    NERFW_CUDA(cudaFuncSetAttribute(tcb::umma_selftest_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tcb::umma_selftest_mn_kernel<<<1, 128, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(at_bf16),
+                                                                    reinterpret_cast<const __nv_bfloat16*>(bt_bf16), n, k, d);
+  NERFW_LAUNCHED();
+  return NERFW_OK;
+}

@@ -1,0 +1,90 @@
+// Layout constants shared by the tensor-core MLP kernels (forward: mlp_tc.cu, backward: mlp_tc_bwd.cu): tile size,
+// packed weight stream, TMEM columns, shared-memory map of the forward pipeline.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace nerfw {
+namespace tc {
+
+using namespace umma;
+
+constexpr int TM = 128;
+constexpr int EPI_WARPS = 8;
+constexpr int PRODUCER_WARP = 8;
+constexpr int MMA_WARP = 9;
+constexpr int THREADS = 320;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+
+constexpr uint32_t BIG_CHUNK = 256 * 128;    // 256 outputs x 64 bf16
+constexpr uint32_t SMALL_CHUNK = 128 * 128;  // 128 outputs x 64 bf16
+constexpr int N_BIG = 30;                    // L0:1, L1-3:12, L4:4+1, L5-7:12
+constexpr int N_SMALL = 5;                   // dir layer: 4 + 1
+constexpr int N_CHUNKS = N_BIG + N_SMALL;
+constexpr size_t W_BYTES = 2ull * (N_BIG * (size_t)BIG_CHUNK + N_SMALL * (size_t)SMALL_CHUNK);  // hi and lo
+
+// fp32 vector block behind the weight chunks
+constexpr int V_PTSB = 0;       // 8 x 256
+constexpr int V_DIRB = 2048;    // 128
+constexpr int V_DENW = 2176;    // 256
+constexpr int V_RGBW = 2432;    // 3 x 128
+constexpr int V_DENB = 2816;    // 1
+constexpr int V_RGBB = 2817;    // 3
+constexpr int V_FLOATS = 2824;  // padded to 16 B
+constexpr size_t PACKED_BYTES = W_BYTES + V_FLOATS * sizeof(float);
+
+// TMEM columns
+constexpr uint32_t COL_ACC = 0;
+constexpr uint32_t COL_AHI = 256;
+constexpr uint32_t COL_ALO = 384;
+
+// shared memory map (offsets from a 1024-aligned base)
+constexpr int NSTAGES = 4;
+constexpr uint32_t SM_PEX_HI = 0;
+constexpr uint32_t SM_PEX_LO = 16384;
+constexpr uint32_t SM_PED_HI = 32768;
+constexpr uint32_t SM_PED_LO = 49152;
+constexpr uint32_t SM_RING = 65536;
+constexpr uint32_t SM_VEC = SM_RING + NSTAGES * BIG_CHUNK;        // 196608
+constexpr uint32_t SM_SIG = SM_VEC + V_FLOATS * 4;                // [2][128] floats
+constexpr uint32_t SM_RGB = SM_SIG + 2 * TM * 4;                  // [128] float4
+constexpr uint32_t SM_BAR = SM_RGB + TM * 16;                     // full[4], empty[4], acc_full, a_ready
+constexpr uint32_t SM_TMEMPTR = SM_BAR + (2 * NSTAGES + 2) * 8;
+constexpr uint32_t SM_TOTAL = SM_TMEMPTR + 16;
+constexpr size_t SMEM_BYTES = SM_TOTAL + 1024;  // slack for the manual 1024-byte alignment
+
+// Chunk i of the stream -> (source matrix, first input column).  Order = consumption order of the MMA thread.
+struct ChunkSrc {
+  int layer;  // 0..7 trunk, 8 = dir layer
+  int col0;   // first input column of this 64-wide K block
+};
+__host__ __device__ inline ChunkSrc chunk_source(int i) {
+  if (i == 0) return {0, 0};
+  if (i < 13) return {1 + (i - 1) / 4, ((i - 1) % 4) * 64};
+  if (i < 18) return {4, (i - 13) * 64};  // i == 17: columns 256.. = enc_x part of the skip layer
+  if (i < 30) return {5 + (i - 18) / 4, ((i - 18) % 4) * 64};
+  return {8, (i - 30) * 64};              // i == 34: columns 256.. = enc_d part
+}
+__host__ __device__ inline size_t chunk_offset(int i) {  // byte offset of the hi copy; lo follows at +size
+  return i < N_BIG ? 2ull * i * BIG_CHUNK : 2ull * N_BIG * BIG_CHUNK + 2ull * (i - N_BIG) * SMALL_CHUNK;
+}
+
+struct Pipe {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+  }
+};
+
+// write one encoded value (hi and optionally lo) into a K-major swizzled operand tile
+template <bool X3>
+__device__ __forceinline__ void put_enc(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t row, uint32_t k, float v) {
+  uint32_t off = sw128_offset(row, k);
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(tile_hi + off) = h;
+  if (X3) *reinterpret_cast<__nv_bfloat16*>(tile_lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+}  // namespace tc
+}  // namespace nerfw

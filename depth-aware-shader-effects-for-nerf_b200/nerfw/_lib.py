@@ -56,6 +56,10 @@ SIGNATURES = {
     "nerfw_mlp_bwd": (C.c_int, [C.POINTER(NerfwWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_int64, C.c_int, C.c_void_p, C.POINTER(NerfwGrads), C.c_void_p, C.c_void_p,
                                  C.c_size_t, C.c_void_p]),
+    "nerfw_mlp_bwd_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "nerfw_mlp_bwd_tc": (C.c_int, [C.POINTER(NerfwWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.POINTER(NerfwGrads), C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "nerfw_composite_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "nerfw_composite_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -65,6 +69,7 @@ SIGNATURES = {
     "nerfw_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nerfw_quantize_u8": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nerfw_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nerfw_selftest_umma_mn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -9,8 +9,18 @@ from typing import Optional
 
 import torch
 
+import os
+
 from . import ops
 from ._lib import MLP_FP32
+
+
+def backward_uses_tensor_cores(mode: int, emb) -> bool:
+    """bf16 tcgen05 backward when the forward ran in a tensor-core mode and the embedding is shared (or absent);
+    NERFW_BWD_MODE=fp32 forces the fp32 CUDA-core backward."""
+    if os.environ.get("NERFW_BWD_MODE", "bf16").lower() == "fp32":
+        return False
+    return mode != MLP_FP32 and (emb is None or emb.shape[0] == 1)
 
 
 def _param_dict(names, tensors):
@@ -33,7 +43,10 @@ def _mlp_backward(ctx, d_raw):
     params = _param_dict(names, saved[k:k + len(names)])
     grads = {n: torch.zeros_like(t) for n, t in params.items()}
     d_emb = torch.zeros_like(emb) if emb is not None else None
-    ops.mlp_bwd(params, grads, p, d, z, emb, d_raw.contiguous(), d_emb)
+    if ctx.packed is not None and backward_uses_tensor_cores(ctx.mode, emb):
+        ops.mlp_bwd_tc(params, grads, ctx.packed, p, d, z, emb, d_raw.contiguous(), d_emb)
+    else:
+        ops.mlp_bwd(params, grads, p, d, z, emb, d_raw.contiguous(), d_emb)
     return grads, d_emb
 
 
@@ -45,6 +58,7 @@ class MlpFn(torch.autograd.Function):
         pd = _param_dict(names, params)
         raw = ops.mlp_fwd(pd, packed, p, d, z, emb, mode)
         ctx.names = names
+        ctx.mode, ctx.packed = mode, packed
         ctx.has_z = z is not None
         ctx.has_emb = emb is not None
         keep = [p, d] + ([z] if z is not None else []) + ([emb] if emb is not None else []) + list(params)
@@ -66,6 +80,7 @@ class RenderFn(torch.autograd.Function):
         raw = ops.mlp_fwd(pd, packed, o, d, z, emb, mode)
         rgb, depth, acc, w = ops.composite_fwd(raw, z, want_weights=True)
         ctx.names = names
+        ctx.mode, ctx.packed = mode, packed
         ctx.has_z = True
         ctx.has_emb = emb is not None
         ctx.set_materialize_grads(False)
@@ -87,6 +102,7 @@ class RenderFn(torch.autograd.Function):
             pass
         c = _Ctx()
         c.names, c.has_z, c.has_emb = ctx.names, True, ctx.has_emb
+        c.mode, c.packed = ctx.mode, ctx.packed
         c.saved_tensors = saved[:-1]
         grads, d_emb = _mlp_backward(c, d_raw)
         return (None, None, None, None, None, d_emb, None) + tuple(grads[n] for n in ctx.names)

@@ -260,6 +260,24 @@ def mlp_bwd(params: dict, grads: dict, p: torch.Tensor, d: torch.Tensor, z: Opti
                                   d_raw.data_ptr(), C.byref(gs), _ptr(d_emb), ws_buf.data_ptr(), wbytes, _stream()))
 
 
+def mlp_bwd_tc(params: dict, grads: dict, packed: torch.Tensor, p: torch.Tensor, d: torch.Tensor,
+               z: Optional[torch.Tensor], emb: Optional[torch.Tensor], d_raw: torch.Tensor,
+               d_emb: Optional[torch.Tensor]) -> None:
+    """Tensor-core (bf16) backward; accumulates into `grads` and d_emb.  Shared or no embedding only."""
+    dev = p.device
+    n_rays = p.shape[0]
+    n_samples = z.shape[1] if z is not None else 1
+    emb_rows = emb.shape[0] if emb is not None else 0
+    wbytes = int(lib().nerfw_mlp_bwd_tc_workspace_bytes(n_rays, n_samples))
+    ws_buf = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    ws = weights_struct(params)
+    gs = weights_struct(grads)
+    with torch.cuda.device(dev):
+        check(lib().nerfw_mlp_bwd_tc(C.byref(ws), packed.data_ptr(), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows,
+                                     n_rays, n_samples, d_raw.data_ptr(), C.byref(gs), _ptr(d_emb), ws_buf.data_ptr(),
+                                     wbytes, _stream()))
+
+
 # ------------------------------------------------------------------------------------------------ compositing
 def composite_fwd(raw: torch.Tensor, z: torch.Tensor, want_weights: bool = True):
     b, n = z.shape
@@ -308,6 +326,17 @@ def quantize_u8(x: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(x.device):
         check(lib().nerfw_quantize_u8(x.data_ptr(), x.numel(), out.data_ptr(), _stream()))
     return out
+
+
+def selftest_umma_mn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
+    """D = At^T Bt for At (K,128), Bt (K,N) bf16: both UMMA operands MN-major (the wgrad form)."""
+    assert at.dtype == torch.bfloat16 and bt.dtype == torch.bfloat16 and at.shape[1] == 128 and at.shape[0] == bt.shape[0]
+    at = at.contiguous()
+    bt = bt.contiguous()
+    d = torch.empty((128, bt.shape[1]), dtype=torch.float32, device=at.device)
+    with torch.cuda.device(at.device):
+        check(lib().nerfw_selftest_umma_mn(at.data_ptr(), bt.data_ptr(), bt.shape[1], at.shape[0], d.data_ptr(), _stream()))
+    return d
 
 
 def selftest_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:

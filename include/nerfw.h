@@ -148,6 +148,14 @@ int nerfw_mlp_bwd(const NerfwWeights* w, const float* pts_or_o, const float* dir
                   const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples, const float* d_raw,
                   const NerfwGrads* grads, float* d_emb, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Tensor-core backward (bf16 operands, fp32 accumulation; stated looser bounds): same contract as nerfw_mlp_bwd, with
+ * the packed weight cache of nerfw_pack_weights; supports no embedding or a shared one (emb_rows == 1).  The workspace
+ * holds the per-tile activation / dZ scratch (1.16 MB per 128 samples). */
+size_t nerfw_mlp_bwd_tc_workspace_bytes(int64_t n_rays, int n_samples);
+int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const float* pts_or_o, const float* dirs, const float* z,
+                     const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples, const float* d_raw,
+                     const NerfwGrads* grads, float* d_emb, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- compositing: the tail of volume_render -- src/render.py:56-80 ------------------------------------
  * raw (B,N,4) = (r,g,b,sigma), z (B,N).  Out: rgb_map (B,3), depth (B,1), acc (B,1) = sum of weights
  * (SURVEY.md F4), weights (B,N) or NULL. */
@@ -177,6 +185,8 @@ int nerfw_quantize_u8(const float* rgb, int64_t n_values, uint8_t* out, void* st
 /* Primitive self-test (tests only): D (128,n) fp32 = A (128,k) bf16 * B (n,k) bf16 ^T through one tcgen05 tile;
  * mode 0 = A from shared memory, 1 = A from tensor memory.  Pins the descriptor / swizzle / TMEM layouts. */
 int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream);
+/* Same with both operands MN-major (the wgrad form): D (128,n) = At^T Bt for At (k,128), Bt (k,n) bf16 row-major. */
+int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, int n, int k, float* d, void* stream);
 
 #ifdef __cplusplus
 }

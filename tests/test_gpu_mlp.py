@@ -26,6 +26,20 @@ def test_umma_primitives(mode, n, k):
     assert err <= 1e-3, err   # exact bf16 products, fp32 accumulation order only
 
 
+@pytest.mark.parametrize("n,k", [(64, 64), (256, 128), (128, 256), (256, 16), (192, 48)])
+def test_umma_mn_major_primitive(n, k):
+    """Both operands MN-major (the wgrad form dW = dZ^T X): D = At^T Bt."""
+    from nerfw import ops
+    g = torch.Generator().manual_seed(n * 7 + k)
+    at = torch.randn(k, 128, generator=g).bfloat16()
+    bt = torch.randn(k, n, generator=g).bfloat16()
+    want = at.float().t() @ bt.float()
+    got = ops.selftest_umma_mn(at.cuda(), bt.cuda())
+    err = maxabs(got, want)
+    record(f"umma_mn_{n}x{k}", maxabs=err)
+    assert err <= 1e-3, err
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
 def test_mlp_forward_golden(cuda_model, golden, mode):
     model, emb = cuda_model
@@ -155,3 +169,42 @@ def test_mlp_backward_vs_oracle_autograd(cuda_model, oracle, state_dict):
         record(f"mlp_bwd_rows{rows}", worst_param_rel=worst, emb_rel=rel_e)
         assert rel_e <= 2e-4, rel_e
     model.zero_grad()
+
+
+@pytest.mark.parametrize("with_emb", [True, False])
+@pytest.mark.parametrize("b,n", [(3, 64), (61, 192), (700, 64)])
+def test_tensor_core_backward_vs_fp32_backward(cuda_model, b, n, with_emb):
+    """tcgen05 backward (bf16 operands, fp32 accumulate) against the fp32 CUDA-core backward on the same inputs and the
+    same cotangent: every parameter gradient within 3e-2 of that tensor's max-abs gradient (bf16 bound), and the two
+    gradients nearly parallel (cosine >= 0.999)."""
+    from nerfw import ops
+    model, emb = cuda_model
+    gen = torch.Generator(device="cuda").manual_seed(b * 13 + n)
+    o = torch.randn(b, 3, device="cuda", generator=gen)
+    d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda", generator=gen), dim=-1)
+    z = torch.sort(torch.rand(b, n, device="cuda", generator=gen) * 4 + 2, dim=-1).values
+    d_raw = torch.randn(b * n, 4, device="cuda", generator=gen)
+    e = emb.unsqueeze(0).contiguous() if with_emb else None
+    names, tensors = model.kernel_params()
+    params = {k: t.detach() for k, t in zip(names, tensors)}
+    packed = model.packed_weights(names, tensors)
+    g_ref = {k: torch.zeros_like(t) for k, t in params.items()}
+    g_tc = {k: torch.zeros_like(t) for k, t in params.items()}
+    de_ref = torch.zeros(1, 32, device="cuda") if with_emb else None
+    de_tc = torch.zeros(1, 32, device="cuda") if with_emb else None
+    ops.mlp_bwd(params, g_ref, o, d, z, e, d_raw, de_ref)
+    ops.mlp_bwd_tc(params, g_tc, packed, o, d, z, e, d_raw, de_tc)
+    worst, worst_cos = 0.0, 1.0
+    for k in params:
+        if not with_emb and k.startswith("appearance"):
+            assert float(g_tc[k].abs().max()) == 0.0
+            continue
+        ref, got = g_ref[k].double(), g_tc[k].double()
+        rel = float((ref - got).abs().max() / (ref.abs().max() + 1e-20))
+        cos = float((ref * got).sum() / (ref.norm() * got.norm() + 1e-30))
+        worst, worst_cos = max(worst, rel), min(worst_cos, cos)
+        assert rel <= 3e-2 and cos >= 0.999, (k, rel, cos)
+    if with_emb:
+        rel = float((de_ref - de_tc).abs().max() / (de_ref.abs().max() + 1e-20))
+        assert rel <= 3e-2, rel
+    record(f"mlp_bwd_tc_{b}x{n}_{'emb' if with_emb else 'noemb'}", worst_rel=worst, worst_cos=worst_cos)
