@@ -663,8 +663,8 @@ __global__ void __launch_bounds__(W2_THREADS, 1) mlp_tc_wgrad_kernel(const __gri
   }
 }
 
-// appearance branch, shared embedding: G = W_rgb^T DL; dW_rgb[c][k] += DL[c] a[k] (a = W_app e + b_app);
-// dW_app[k][q] += G[k] e[q]; db_app[k] += G[k]; d_emb[q] += sum_k G[k] W_app[k][q]
+// appearance branch, shared embedding: G = W_rgb^T DL; dW_app[k][q] += G[k] e[q]; db_app[k] += G[k];
+// d_emb[q] += sum_k G[k] W_app[k][q].  (dW_rgb already contains the appearance term: pass 2 reduces against hd + a.)
 __global__ void __launch_bounds__(128) app_bwd_shared_kernel(NerfwWeights w, NerfwGrads g, const float* __restrict__ emb,
                                                              const float* __restrict__ app_vec,
                                                              const float* __restrict__ dl, float* __restrict__ d_emb) {
@@ -673,10 +673,7 @@ __global__ void __launch_bounds__(128) app_bwd_shared_kernel(NerfwWeights w, Ner
   const float d0 = dl[0], d1 = dl[1], d2 = dl[2];
   const float G = d0 * __ldg(w.rgb_w + k) + d1 * __ldg(w.rgb_w + 128 + k) + d2 * __ldg(w.rgb_w + 256 + k);
   gk[k] = G;
-  const float a = app_vec[k];
-  atomicAdd(g.rgb_w + k, d0 * a);
-  atomicAdd(g.rgb_w + 128 + k, d1 * a);
-  atomicAdd(g.rgb_w + 256 + k, d2 * a);
+  (void)app_vec;
   for (int q = 0; q < NERFW_APP_DIM; ++q) atomicAdd(g.app_w + k * NERFW_APP_DIM + q, G * __ldg(emb + q));
   atomicAdd(g.app_b + k, G);
   __syncthreads();

@@ -152,3 +152,31 @@ def test_training_gradients_golden(cuda_model, oracle, golden, manifest):
     record("train_grads_64", worst_rel=worst, emb_rel=rel_e, loss=float(loss))
     assert rel_e <= 5e-4
     model.zero_grad()
+
+
+def test_render_frame_matches_chunked_reference_pattern(cuda_model, oracle):
+    """Whole-frame call == the reference's chunk loop (render_aligned_spiral.py:136-158), and the uint8 image equals
+    (rgb * 255).astype(uint8) of render_aligned_spiral.py:161."""
+    import nerfw
+    from nerfw.frame import quantize_frame, render_frame, render_path
+    from nerfw.camera import aligned_spiral_poses, blender_focal
+    model, emb = cuda_model
+    pose = aligned_spiral_poses(120, 2, "x", "chair")[7]
+    hh = ww = 48
+    focal = blender_focal(ww)
+    rgb, depth, acc = render_frame(model, hh, ww, focal, pose, 2.0, 6.0, 64, 0, appearance_embedding=emb)
+    o, d = nerfw.get_rays(hh, ww, focal, torch.from_numpy(pose).cuda())
+    chunks = []
+    with torch.no_grad():
+        for j in range(0, hh * ww, 1000):
+            c, _, _ = nerfw.volume_render(model, o.reshape(-1, 3)[j:j + 1000], d.reshape(-1, 3)[j:j + 1000], 2.0, 6.0, 64, 0,
+                                          appearance_embedding=emb, perturb=False)
+            chunks.append(c.cpu())
+    want = torch.cat(chunks).reshape(hh, ww, 3)
+    assert torch.equal(rgb.cpu(), want)
+    rgb8, depth8 = quantize_frame(rgb, depth)
+    assert np.array_equal(rgb8.cpu().numpy(), (want * 255).numpy().astype(np.uint8))
+    dn = depth.cpu().numpy()
+    assert np.array_equal(depth8.cpu().numpy(), ((dn - dn.min()) / (dn.max() - dn.min()) * 255).astype(np.uint8))
+    frames = list(render_path(model, aligned_spiral_poses(3, 1), 16, 16, blender_focal(16), 2.0, 6.0, 16, 16, appearance_embedding=emb))
+    assert [f[0] for f in frames] == [0, 1, 2] and frames[0][1].shape == (16, 16, 3) and frames[0][1].dtype == np.uint8
