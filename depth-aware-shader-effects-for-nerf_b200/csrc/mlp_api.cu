@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "mlp_common.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_tc_layout.cuh"
 
 using namespace nerfw;
 
@@ -22,7 +23,8 @@ extern "C" size_t nerfw_mlp_workspace_bytes(int64_t n_rays, int64_t emb_rows) {
 
 extern "C" int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const float* pts_or_o, const float* dirs,
                              const float* z, const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples,
-                             int mode, float* raw, void* workspace, size_t workspace_bytes, void* stream) {
+                             int mode, float* raw, void* relu_masks, void* workspace, size_t workspace_bytes,
+                             void* stream) {
   int rc = check_weights(w, "nerfw_mlp_fwd");
   if (rc) return rc;
   NERFW_REQUIRE(n_rays >= 0 && n_samples >= 1, "nerfw_mlp_fwd: bad shape n_rays=%lld n_samples=%d", (long long)n_rays, n_samples);
@@ -56,15 +58,21 @@ extern "C" int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const fl
   }
   switch (mode) {
     case NERFW_MLP_FP32:
+      NERFW_REQUIRE(!relu_masks, "nerfw_mlp_fwd: relu_masks are produced by the tensor-core modes only");
       return launch_mlp_ffma_fwd(*w, src, app_off, total, raw, as_stream(stream));
     case NERFW_MLP_BF16X3:
     case NERFW_MLP_BF16:
       NERFW_REQUIRE(packed, "nerfw_mlp_fwd: tensor-core modes need the packed weight cache (nerfw_pack_weights)");
-      return launch_mlp_tc_fwd(*w, packed, src, app_off, total, mode == NERFW_MLP_BF16X3, raw, as_stream(stream));
+      return launch_mlp_tc_fwd(*w, packed, src, app_off, total, mode == NERFW_MLP_BF16X3, raw, relu_masks, as_stream(stream));
     default:
       set_error("nerfw_mlp_fwd: unknown mode %d", mode);
       return NERFW_EINVAL;
   }
+}
+
+extern "C" size_t nerfw_mlp_mask_bytes(int64_t n_rays, int n_samples) {
+  const int64_t total = n_rays * (int64_t)(n_samples > 0 ? n_samples : 1);
+  return (size_t)ceil_div64(total, tc::TM) * tc::MASK_WORDS_PER_TILE * sizeof(uint32_t);
 }
 
 extern "C" size_t nerfw_packed_bytes(void) { return mlp_tc_packed_total_bytes(); }

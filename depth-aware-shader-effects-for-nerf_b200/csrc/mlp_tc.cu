@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) app_offset_kernel(NerfwWeights w, const f
 template <bool X3>
 __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* __restrict__ packed, SampleSource src,
                                                                  const float4* __restrict__ app_off, int64_t n_total,
-                                                                 float4* __restrict__ raw) {
+                                                                 float4* __restrict__ raw, uint32_t* __restrict__ masks) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -283,6 +283,12 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bias[col + j], 0.f);
+          if (masks) {  // ReLU gates for the backward pass (training): bit j <-> column col + j
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+            masks[mask_index(tile, layer, row, ch, q)] = bits;
+          }
           if (layer == NERFW_LAYERS - 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) sig = fmaf(v[j], vec[V_DENW + col + j], sig);
@@ -320,11 +326,15 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
         tmem_ld32(tlane + COL_ACC + col, r);
         tmem_wait_ld();
 #pragma unroll
+        uint32_t bits = 0;
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
           float hv = fmaxf(__uint_as_float(r[j]) + vec[V_DIRB + col + j], 0.f);
+          bits |= (hv > 0.f ? 1u : 0u) << j;
 #pragma unroll
           for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv, vec[V_RGBW + c * 128 + col + j], p3[c]);
         }
+        if (masks) masks[mask_index(tile, NERFW_LAYERS, row, ch, q)] = bits;
       }
       tc_fence_before();
       if (ch == 1) rgb_part[row] = make_float4(p3[0], p3[1], p3[2], 0.f);
@@ -445,7 +455,7 @@ int launch_app_offset(const NerfwWeights& w, const float* emb, int64_t emb_rows,
 }
 
 int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSource& src, const float* app_off,
-                      int64_t n_total, bool x3, float* raw, cudaStream_t stream) {
+                      int64_t n_total, bool x3, float* raw, void* relu_masks, cudaStream_t stream) {
   (void)w;
   static thread_local bool attr_set = false;
   if (!attr_set) {
@@ -458,9 +468,9 @@ int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSou
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   const float4* ao = reinterpret_cast<const float4*>(app_off);
   if (x3)
-    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw));
+    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks));
   else
-    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw));
+    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks));
   NERFW_LAUNCHED();
   return NERFW_OK;
 }

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
                                                                        const float* __restrict__ app_vec,
                                                                        const float4* __restrict__ d_raw, int64_t n_total,
                                                                        uint8_t* __restrict__ scratch,
-                                                                       float* __restrict__ dl_acc) {
+                                                                       float* __restrict__ dl_acc,
+                                                                       const uint32_t* __restrict__ fwd_masks) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
             v[j] = fmaxf(__uint_as_float(r[j]) + bias[col + j], 0.f);
             bits |= (v[j] > 0.f ? 1u : 0u) << j;
           }
-          mw[q] = bits;
+          if (!fwd_masks) mw[q] = bits;
           if (layer == NERFW_LAYERS - 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) sig = fmaf(v[j], vec[V_DENW + col + j], sig);
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
 #pragma unroll
         for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(hv[2 * j] + appv[col + 2 * j], hv[2 * j + 1] + appv[col + 2 * j + 1]);
         store_row32(tsc, XB_HDT, row, col, ph);
-        hmask[q] = bits;
+        hmask[q] = fwd_masks ? __ldg(fwd_masks + mask_index(tile, NERFW_LAYERS, row, ch, q)) : bits;
       }
       tc_fence_before();
       rgb_part[ch * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
           uint32_t r[32];
           tmem_ld32(tlane + COL_ACC + col, r);
           tmem_wait_ld();
-          const uint32_t bits = mw[q];
+          const uint32_t bits = fwd_masks ? __ldg(fwd_masks + mask_index(tile, l, row, ch, q)) : mw[q];
           uint32_t ph[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -771,8 +772,8 @@ extern "C" size_t nerfw_mlp_bwd_tc_workspace_bytes(int64_t n_rays, int n_samples
 // Same contract as nerfw_mlp_bwd (include/nerfw.h), tensor-core arithmetic; shared (emb_rows == 1) or no embedding only.
 extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const float* pts_or_o, const float* dirs,
                                 const float* z, const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples,
-                                const float* d_raw, const NerfwGrads* grads, float* d_emb, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                const float* d_raw, const void* relu_masks, const NerfwGrads* grads, float* d_emb,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   NERFW_REQUIRE(w && grads && packed, "nerfw_mlp_bwd_tc: null weights, grads or packed weights");
   for (int i = 0; i < NERFW_LAYERS; ++i)
     NERFW_REQUIRE(w->pts_w[i] && w->pts_b[i] && grads->pts_w[i] && grads->pts_b[i], "nerfw_mlp_bwd_tc: null pts_linears.%d parameter or gradient", i);
@@ -827,7 +828,8 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   int64_t grid1 = ntiles < sms ? ntiles : sms;
   tcb::mlp_tc_bwd_pass1_kernel<<<(unsigned)grid1, tc::THREADS, tcb::SMEM1_BYTES, st>>>(
       reinterpret_cast<const uint8_t*>(packed), src, emb ? reinterpret_cast<const float4*>(app_off) : nullptr,
-      emb ? app_vec : nullptr, reinterpret_cast<const float4*>(d_raw), total, scratch, emb ? dl_acc : nullptr);
+      emb ? app_vec : nullptr, reinterpret_cast<const float4*>(d_raw), total, scratch, emb ? dl_acc : nullptr,
+      reinterpret_cast<const uint32_t*>(relu_masks));
   NERFW_LAUNCHED();
 
   // ---- pass-2 plan: one weight block and one contiguous tile range per CTA, CTAs shared out by bytes per tile ----

@@ -86,5 +86,12 @@ __device__ __forceinline__ void put_enc(uint8_t* tile_hi, uint8_t* tile_lo, uint
   if (X3) *reinterpret_cast<__nv_bfloat16*>(tile_lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// ReLU gate words written by the forward kernel in training mode and read by the backward kernel:
+// [tile][layer 0..8][row][column half][4 words of 32 gates]; layer 8 = direction layer (2 words per half used).
+constexpr size_t MASK_WORDS_PER_TILE = 9ull * TM * 8;
+__host__ __device__ inline size_t mask_index(int64_t tile, int layer, uint32_t row, uint32_t ch, int q) {
+  return ((size_t)tile * 9 + layer) * (TM * 8) + row * 8 + ch * 4 + q;
+}
+
 }  // namespace tc
 }  // namespace nerfw

@@ -50,16 +50,18 @@ SIGNATURES = {
     "nerfw_packed_bytes": (C.c_size_t, []),
     "nerfw_pack_weights": (C.c_int, [C.POINTER(NerfwWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nerfw_mlp_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "nerfw_mlp_mask_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "nerfw_mlp_fwd": (C.c_int, [C.POINTER(NerfwWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                 C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                 C.c_void_p]),
     "nerfw_mlp_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int64]),
     "nerfw_mlp_bwd": (C.c_int, [C.POINTER(NerfwWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_int64, C.c_int, C.c_void_p, C.POINTER(NerfwGrads), C.c_void_p, C.c_void_p,
                                  C.c_size_t, C.c_void_p]),
     "nerfw_mlp_bwd_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "nerfw_mlp_bwd_tc": (C.c_int, [C.POINTER(NerfwWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.POINTER(NerfwGrads), C.c_void_p,
-                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+                                    C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(NerfwGrads),
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nerfw_composite_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "nerfw_composite_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -44,7 +44,7 @@ def _mlp_backward(ctx, d_raw):
     grads = {n: torch.zeros_like(t) for n, t in params.items()}
     d_emb = torch.zeros_like(emb) if emb is not None else None
     if ctx.packed is not None and backward_uses_tensor_cores(ctx.mode, emb):
-        ops.mlp_bwd_tc(params, grads, ctx.packed, p, d, z, emb, d_raw.contiguous(), d_emb)
+        ops.mlp_bwd_tc(params, grads, ctx.packed, p, d, z, emb, d_raw.contiguous(), d_emb, ctx.masks)
     else:
         ops.mlp_bwd(params, grads, p, d, z, emb, d_raw.contiguous(), d_emb)
     return grads, d_emb
@@ -56,7 +56,11 @@ class MlpFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mode, names, p, d, z, emb, packed, *params):
         pd = _param_dict(names, params)
-        raw = ops.mlp_fwd(pd, packed, p, d, z, emb, mode)
+        ctx.masks = None
+        if packed is not None and backward_uses_tensor_cores(mode, emb):
+            raw, ctx.masks = ops.mlp_fwd(pd, packed, p, d, z, emb, mode, want_masks=True)
+        else:
+            raw = ops.mlp_fwd(pd, packed, p, d, z, emb, mode)
         ctx.names = names
         ctx.mode, ctx.packed = mode, packed
         ctx.has_z = z is not None
@@ -77,7 +81,11 @@ class RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mode, names, o, d, z, emb, packed, *params):
         pd = _param_dict(names, params)
-        raw = ops.mlp_fwd(pd, packed, o, d, z, emb, mode)
+        ctx.masks = None
+        if packed is not None and backward_uses_tensor_cores(mode, emb):
+            raw, ctx.masks = ops.mlp_fwd(pd, packed, o, d, z, emb, mode, want_masks=True)
+        else:
+            raw = ops.mlp_fwd(pd, packed, o, d, z, emb, mode)
         rgb, depth, acc, w = ops.composite_fwd(raw, z, want_weights=True)
         ctx.names = names
         ctx.mode, ctx.packed = mode, packed
@@ -102,7 +110,7 @@ class RenderFn(torch.autograd.Function):
             pass
         c = _Ctx()
         c.names, c.has_z, c.has_emb = ctx.names, True, ctx.has_emb
-        c.mode, c.packed = ctx.mode, ctx.packed
+        c.mode, c.packed, c.masks = ctx.mode, ctx.packed, ctx.masks
         c.saved_tensors = saved[:-1]
         grads, d_emb = _mlp_backward(c, d_raw)
         return (None, None, None, None, None, d_emb, None) + tuple(grads[n] for n in ctx.names)

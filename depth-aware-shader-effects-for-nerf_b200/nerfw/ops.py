@@ -225,8 +225,9 @@ def pack_weights(params: dict, out: Optional[torch.Tensor] = None) -> torch.Tens
 
 
 def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: torch.Tensor, z: Optional[torch.Tensor],
-            emb: Optional[torch.Tensor], mode: int) -> torch.Tensor:
-    """raw (S,4) = (r,g,b,sigma).  p,d: (B,3) rays with z (B,N), or (S,3) samples with z None."""
+            emb: Optional[torch.Tensor], mode: int, want_masks: bool = False):
+    """raw (S,4) = (r,g,b,sigma).  p,d: (B,3) rays with z (B,N), or (S,3) samples with z None.
+    want_masks (tensor-core modes): also return the ReLU gate words for nerfw_mlp_bwd_tc -> (raw, masks)."""
     dev = p.device
     n_rays = p.shape[0]
     n_samples = z.shape[1] if z is not None else 1
@@ -238,9 +239,15 @@ def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: to
     wbytes = int(lib().nerfw_mlp_workspace_bytes(n_rays, emb_rows))
     ws_buf = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     ws = weights_struct(params)
+    masks = None
+    if want_masks:
+        masks = torch.empty(int(lib().nerfw_mlp_mask_bytes(n_rays, n_samples)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         check(lib().nerfw_mlp_fwd(C.byref(ws), _ptr(packed), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows,
-                                  n_rays, n_samples, int(mode), raw.data_ptr(), ws_buf.data_ptr(), wbytes, _stream()))
+                                  n_rays, n_samples, int(mode), raw.data_ptr(), _ptr(masks), ws_buf.data_ptr(), wbytes,
+                                  _stream()))
+    if want_masks:
+        return raw, masks
     return raw
 
 
@@ -262,8 +269,9 @@ def mlp_bwd(params: dict, grads: dict, p: torch.Tensor, d: torch.Tensor, z: Opti
 
 def mlp_bwd_tc(params: dict, grads: dict, packed: torch.Tensor, p: torch.Tensor, d: torch.Tensor,
                z: Optional[torch.Tensor], emb: Optional[torch.Tensor], d_raw: torch.Tensor,
-               d_emb: Optional[torch.Tensor]) -> None:
-    """Tensor-core (bf16) backward; accumulates into `grads` and d_emb.  Shared or no embedding only."""
+               d_emb: Optional[torch.Tensor], masks: Optional[torch.Tensor] = None) -> None:
+    """Tensor-core (bf16) backward; accumulates into `grads` and d_emb.  Shared or no embedding only.
+    masks: the ReLU gates returned by mlp_fwd(want_masks=True)."""
     dev = p.device
     n_rays = p.shape[0]
     n_samples = z.shape[1] if z is not None else 1
@@ -274,8 +282,8 @@ def mlp_bwd_tc(params: dict, grads: dict, packed: torch.Tensor, p: torch.Tensor,
     gs = weights_struct(grads)
     with torch.cuda.device(dev):
         check(lib().nerfw_mlp_bwd_tc(C.byref(ws), packed.data_ptr(), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows,
-                                     n_rays, n_samples, d_raw.data_ptr(), C.byref(gs), _ptr(d_emb), ws_buf.data_ptr(),
-                                     wbytes, _stream()))
+                                     n_rays, n_samples, d_raw.data_ptr(), _ptr(masks), C.byref(gs), _ptr(d_emb),
+                                     ws_buf.data_ptr(), wbytes, _stream()))
 
 
 # ------------------------------------------------------------------------------------------------ compositing

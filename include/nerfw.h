@@ -135,11 +135,13 @@ int nerfw_pack_weights(const NerfwWeights* w, void* packed, size_t packed_bytes,
  * (per ray, src/render.py:39-44; per sample when z == NULL).
  * out: raw (S,4) = (r,g,b,sigma) after sigmoid / relu (src/models.py:138,160).
  * `packed` is required for the BF16X3/BF16 modes (else may be NULL); `workspace` must hold
- * nerfw_mlp_workspace_bytes(n_rays, emb_rows) bytes. */
+ * nerfw_mlp_workspace_bytes(n_rays, emb_rows) bytes.  relu_masks (NULL, or nerfw_mlp_mask_bytes() bytes; tensor-core modes
+ * only) receives the ReLU gates of every layer so that nerfw_mlp_bwd_tc gates its gradients exactly like this forward. */
 size_t nerfw_mlp_workspace_bytes(int64_t n_rays, int64_t emb_rows);
+size_t nerfw_mlp_mask_bytes(int64_t n_rays, int n_samples);
 int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const float* pts_or_o, const float* dirs,
                   const float* z, const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples, int mode,
-                  float* raw, void* workspace, size_t workspace_bytes, void* stream);
+                  float* raw, void* relu_masks, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the above (autograd of src/models.py:105-162): d_raw (S,4) in; accumulates (+=) into grads and,
  * if d_emb != NULL, into d_emb (emb_rows,32).  fp32 CUDA-core arithmetic. */
@@ -150,11 +152,13 @@ int nerfw_mlp_bwd(const NerfwWeights* w, const float* pts_or_o, const float* dir
 
 /* Tensor-core backward (bf16 operands, fp32 accumulation; stated looser bounds): same contract as nerfw_mlp_bwd, with
  * the packed weight cache of nerfw_pack_weights; supports no embedding or a shared one (emb_rows == 1).  The workspace
- * holds the per-tile activation / dZ scratch (1.16 MB per 128 samples). */
+ * holds the per-tile activation / dZ scratch (1.16 MB per 128 samples).  relu_masks: the gates written by nerfw_mlp_fwd
+ * (recommended: gradients then follow the forward that produced the loss), or NULL to use the bf16 recompute's own. */
 size_t nerfw_mlp_bwd_tc_workspace_bytes(int64_t n_rays, int n_samples);
 int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const float* pts_or_o, const float* dirs, const float* z,
                      const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples, const float* d_raw,
-                     const NerfwGrads* grads, float* d_emb, void* workspace, size_t workspace_bytes, void* stream);
+                     const void* relu_masks, const NerfwGrads* grads, float* d_emb, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* ---- compositing: the tail of volume_render -- src/render.py:56-80 ------------------------------------
  * raw (B,N,4) = (r,g,b,sigma), z (B,N).  Out: rgb_map (B,3), depth (B,1), acc (B,1) = sum of weights
