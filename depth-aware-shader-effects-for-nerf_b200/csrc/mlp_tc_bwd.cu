@@ -17,6 +17,7 @@
 #include "mlp_common.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc_layout.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace nerfw {
@@ -461,9 +462,10 @@ struct WgradPlan {
   float* d_density_b;
   float* d_rgb_w;
   float* d_rgb_b;
+  int debug;  // bit 0: skip MMAs, bit 1: skip CUDA-core reductions (profiling only)
 };
 
-constexpr int W2_THREADS = 192;          // warp 0 producer, warp 1 MMA, warps 2..5 reducers / flush
+constexpr int W2_THREADS = 320;          // warp 0 producer, warp 1 MMA, warps 2..9 reducers / flush
 constexpr int W2_STAGES = 3;
 constexpr uint32_t W2_PIECE = 8192;      // 64 samples x 64 features
 constexpr uint32_t W2_DZ = 0;            // up to 4 pieces
@@ -496,13 +498,14 @@ __global__ void __launch_bounds__(W2_THREADS, 1) mlp_tc_wgrad_kernel(const __gri
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
   const WgradBlock& wb = plan.blocks[plan.unit_block[blockIdx.x]];
   const int t0 = plan.unit_t0[blockIdx.x], t1 = plan.unit_t1[blockIdx.x];
-  const bool has_mma = wb.x_block >= 0 && !(wb.flags & 4);
+  const bool has_mma = wb.x_block >= 0 && !(wb.flags & 4) && !(plan.debug & 1);
+  const int rflags = (plan.debug & 2) ? 0 : wb.flags;
   const int n_dz = 2 * wb.n_mhalves;
   const int N = 64 * wb.x_nblocks;
   const bool need_dls = (wb.flags & 6) != 0;
 
   if (tid == 0) {
-    for (int i = 0; i < W2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 128); }
+    for (int i = 0; i < W2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 256); }
     mbar_init(done, 1);
     fence_mbar_init();
   }
@@ -557,95 +560,106 @@ __global__ void __launch_bounds__(W2_THREADS, 1) mlp_tc_wgrad_kernel(const __gri
       if (has_mma) mma_commit(done); else mbar_arrive(done);
     }
   } else {
-    // ---- reducers: bias column sums / head gradients from the shared-memory tiles, then the accumulator flush ----
-    const int rt = tid - 64;  // 0..127
-    float bsum[2] = {0.f, 0.f};             // bias: output columns 2 rt, 2 rt + 1
-    float dsw[2] = {0.f, 0.f};              // density head: input columns 2 rt, 2 rt + 1
-    float rg[3] = {0.f, 0.f, 0.f};          // rgb head: column rt, three channels
-    float hb[4] = {0.f, 0.f, 0.f, 0.f};     // rgb / density bias partial sums (threads 0..2 / thread 0)
+    // ---- reducers (8 warps): bias / head gradients as column reductions of the shared-memory tiles, 16 bytes
+    // (8 bf16 columns) per load, 8 rows of every 64-row stage per thread; then the accumulator flush ----
+    const int rt = tid - 64;           // 0..255
+    const int grp = rt & 31;           // 8-column group: columns 8 grp .. 8 grp + 7  (256 columns = 4 pieces x 8 chunks)
+    const int rset = rt >> 5;          // rows 8 rset .. 8 rset + 7 of the stage
+    float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias sums, or density-head sums (flag 2 uses acc8b)
+    float acc8b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float rg[3][8];                                                // rgb head: 3 channels x 8 columns
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rg[c][j] = 0.f;
+    float hb[4] = {0.f, 0.f, 0.f, 0.f};  // sums of d logits (x,y,z) and d sigma_pre over this thread's rows (grp == 0 only)
     int stage = 0;
     uint32_t phase = 0;
-    const int c2 = 2 * rt;
+    const int ncols_out = 128 * wb.n_mhalves;
+    auto unpack8 = [](const uint4& v, float (&f)[8]) {
+      f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+      f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+      f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+      f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+    };
     for (int it = 0; it < n_stages_total; ++it) {
       mbar_wait(&full[stage], phase);
       const uint8_t* st = sm + stage * W2_STAGE;
       const float4* dls = reinterpret_cast<const float4*>(st + W2_DLS);
-      if ((wb.flags & 1) && c2 < 128 * wb.n_mhalves) {
-        const uint8_t* piece = st + W2_DZ + (c2 >> 6) * W2_PIECE;
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-          uint32_t v = *reinterpret_cast<const uint32_t*>(piece + sw128_offset((uint32_t)r, (uint32_t)(c2 & 63)));
-          float2 f = bf16x2_to_float2(v);
-          a0 += f.x; a1 += f.y;
-        }
-        bsum[0] += a0; bsum[1] += a1;
-      }
-      if (wb.flags & 2) {
-        // d density_w[k] += sum_s dsig[s] * h8[s][k]; thread rt owns input columns 2 rt, 2 rt + 1
-        const uint8_t* piece = st + W2_X + (c2 >> 6) * W2_PIECE;
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-          uint32_t v = *reinterpret_cast<const uint32_t*>(piece + sw128_offset((uint32_t)r, (uint32_t)(c2 & 63)));
-          float2 f = bf16x2_to_float2(v);
-          float ds = dls[r].w;
-          a0 = fmaf(ds, f.x, a0); a1 = fmaf(ds, f.y, a1);
-        }
-        dsw[0] += a0; dsw[1] += a1;
-        if (rt == 0) {
-          float a = 0.f;
-          for (int r = 0; r < 64; ++r) a += dls[r].w;
-          hb[3] += a;
+      if ((rflags & 1) && 8 * grp < ncols_out) {
+        const uint8_t* piece = st + W2_DZ + (grp >> 3) * W2_PIECE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t r = rset * 8 + i;
+          const uint4 v = *reinterpret_cast<const uint4*>(piece + sw128_offset(r, (uint32_t)(grp & 7) * 8));
+          float f[8];
+          unpack8(v, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc8[j] += f[j];
         }
       }
-      if (wb.flags & 4) {
-        // d rgb_w[c][k] += sum_s dlog[s][c] * hdt[s][k]; thread rt owns input column rt (128 columns = 2 pieces)
-        const uint8_t* piece = st + W2_X + (rt >> 6) * W2_PIECE;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-          float h = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(piece + sw128_offset((uint32_t)r, (uint32_t)(rt & 63))));
-          float4 d = dls[r];
-          a0 = fmaf(d.x, h, a0); a1 = fmaf(d.y, h, a1); a2 = fmaf(d.z, h, a2);
+      if (rflags & 2) {  // d density_w[k] += sum_s dsig[s] h8[s][k]   (X = H8, 256 columns)
+        const uint8_t* piece = st + W2_X + (grp >> 3) * W2_PIECE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t r = rset * 8 + i;
+          const uint4 v = *reinterpret_cast<const uint4*>(piece + sw128_offset(r, (uint32_t)(grp & 7) * 8));
+          const float ds = dls[r].w;
+          float f[8];
+          unpack8(v, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc8b[j] = fmaf(ds, f[j], acc8b[j]);
+          if (grp == 0) hb[3] += ds;
         }
-        rg[0] += a0; rg[1] += a1; rg[2] += a2;
-        if (rt < 3) {
-          float a = 0.f;
-          for (int r = 0; r < 64; ++r) {
-            float4 d = dls[r];
-            a += rt == 0 ? d.x : (rt == 1 ? d.y : d.z);
+      }
+      if ((rflags & 4) && grp < 16) {  // d rgb_w[c][k] += sum_s dlog[s][c] hdt[s][k]   (X = hd + appearance, 128 columns)
+        const uint8_t* piece = st + W2_X + (grp >> 3) * W2_PIECE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t r = rset * 8 + i;
+          const uint4 v = *reinterpret_cast<const uint4*>(piece + sw128_offset(r, (uint32_t)(grp & 7) * 8));
+          const float4 dl = dls[r];
+          float f[8];
+          unpack8(v, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            rg[0][j] = fmaf(dl.x, f[j], rg[0][j]);
+            rg[1][j] = fmaf(dl.y, f[j], rg[1][j]);
+            rg[2][j] = fmaf(dl.z, f[j], rg[2][j]);
           }
-          hb[rt] += a;
+          if (grp == 0) { hb[0] += dl.x; hb[1] += dl.y; hb[2] += dl.z; }
         }
       }
       mbar_arrive(&empty[stage]);
       if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
     }
-    // ---- flush ----
-    if ((wb.flags & 1) && c2 < 128 * wb.n_mhalves) {
-      atomicAdd(wb.db + c2, bsum[0]);
-      atomicAdd(wb.db + c2 + 1, bsum[1]);
-    }
-    if (wb.flags & 2) {
-      atomicAdd(plan.d_density_w + 2 * rt, dsw[0]);
-      atomicAdd(plan.d_density_w + 2 * rt + 1, dsw[1]);
-      if (rt == 0) atomicAdd(plan.d_density_b, hb[3]);
-    }
-    if (wb.flags & 4) {
+    // ---- flush the CUDA-core partial sums (each of the 8 row sets holds a partial of the same columns) ----
+    if ((rflags & 1) && 8 * grp < ncols_out) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) atomicAdd(plan.d_rgb_w + c * 128 + rt, rg[c]);
-      if (rt < 3) atomicAdd(plan.d_rgb_b + rt, hb[rt]);
+      for (int j = 0; j < 8; ++j) atomicAdd(wb.db + 8 * grp + j, acc8[j]);
+    }
+    if (rflags & 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(plan.d_density_w + 8 * grp + j, acc8b[j]);
+      if (grp == 0) atomicAdd(plan.d_density_b, hb[3]);
+    }
+    if ((rflags & 4) && grp < 16) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(plan.d_rgb_w + c * 128 + 8 * grp + j, rg[c][j]);
+      if (grp == 0) { atomicAdd(plan.d_rgb_b + 0, hb[0]); atomicAdd(plan.d_rgb_b + 1, hb[1]); atomicAdd(plan.d_rgb_b + 2, hb[2]); }
     }
     mbar_wait(done, 0);
     tc_fence_after();
     if (has_mma && n_stages_total > 0) {
       const uint32_t quad = warp & 3;
+      const int chalf = (warp - 2) >> 2;  // the two warps of a lane quadrant take alternate 32-column groups
       const uint32_t tl = tmem + ((quad * 32) << 16);
       for (int h = 0; h < wb.n_mhalves; ++h) {
         const int o = h * 128 + quad * 32 + lane;
         float* dst = wb.dW + (size_t)o * wb.ld + wb.k0;
-        for (int c0 = 0; c0 < N; c0 += 32) {
+        for (int c0 = 32 * chalf; c0 < N; c0 += 64) {
           uint32_t r[32];
           tmem_ld32(tl + (uint32_t)(h * N + c0), r);
           tmem_wait_ld();
@@ -741,6 +755,43 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_mn_kernel(const __nv_bfl
       tmem_wait_ld();
       for (int j = 0; j < 32; ++j) D[(size_t)tid * N + c0 + j] = __uint_as_float(r[j]);
     }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// Issue-rate probe: `reps` x 16 MMAs (M=128, N, K=16) over resident operand tiles, cycles measured with clock64.
+// mode 0: K-major SS, 1: K-major TS (A in TMEM), 2: MN-major SS.  Operand contents are irrelevant (zeros).
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int mode, int N, int reps, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 65536 + 131072);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (65536 + 131072) / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (tid == 0) {
+    const uint32_t sa = smem_u32(sm), sb = smem_u32(sm + 65536);
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int kb = 0; kb < 4; ++kb) {
+        for (int k = 0; k < 4; ++k) {
+          if (mode == 0) mma_ss(tmem, smem_desc_sw128(sa + kb * 16384) + 2 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_bf16(128, (uint32_t)N), 1u);
+          else if (mode == 1) mma_ts(tmem, tmem + COL_AHI + 32 * kb + 8 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_bf16(128, (uint32_t)N), 1u);
+          else mma_ss(tmem, smem_desc_sw128_mn(sa, 8192) + 128 * (kb * 4 + k) % 512, smem_desc_sw128_mn(sb, 8192) + 128 * ((kb * 4 + k) % 4), idesc_bf16_mn(128, (uint32_t)N), 1u);
+        }
+      }
+    }
+    mma_commit(bar);
+    mbar_wait(bar, 0);
+    cycles[0] = clock64() - t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -854,6 +905,10 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   plan.d_density_b = grads->density_b;
   plan.d_rgb_w = grads->rgb_w;
   plan.d_rgb_b = grads->rgb_b;
+  {
+    const char* dbg = getenv("NERFW_WGRAD_DEBUG");
+    plan.debug = dbg ? atoi(dbg) : 0;
+  }
   double cost[13], csum = 0;
   for (int b = 0; b < nb; ++b) {
     const tcb::WgradBlock& wb = plan.blocks[b];
@@ -920,6 +975,20 @@ extern "C" int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, 
   }
   tcb::umma_selftest_mn_kernel<<<1, 128, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(at_bf16),
                                                                     reinterpret_cast<const __nv_bfloat16*>(bt_bf16), n, k, d);
+  NERFW_LAUNCHED();
+  return NERFW_OK;
+}
+
+// Tensor-pipe issue-rate probe (tests / DESIGN.md numbers): cycles for reps x 16 MMAs of shape 128 x n x 16.
+extern "C" int nerfw_selftest_umma_rate(int mode, int n, int reps, long long* cycles_dev, void* stream) {
+  NERFW_REQUIRE(cycles_dev && mode >= 0 && mode <= 2 && n >= 16 && n <= 256 && n % 16 == 0 && reps >= 1, "nerfw_selftest_umma_rate: bad arguments");
+  const size_t smem = 65536 + 131072 + 64 + 1024;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    NERFW_CUDA(cudaFuncSetAttribute(tcb::umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tcb::umma_rate_kernel<<<1, 128, smem, as_stream(stream)>>>(mode, n, reps, cycles_dev);
   NERFW_LAUNCHED();
   return NERFW_OK;
 }

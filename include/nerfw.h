@@ -191,6 +191,9 @@ int nerfw_quantize_u8(const float* rgb, int64_t n_values, uint8_t* out, void* st
 int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream);
 /* Same with both operands MN-major (the wgrad form): D (128,n) = At^T Bt for At (k,128), Bt (k,n) bf16 row-major. */
 int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, int n, int k, float* d, void* stream);
+/* Tensor-pipe issue-rate probe: device cycles (int64 at cycles_dev) for reps x 16 MMAs of shape 128 x n x 16;
+ * mode 0 = K-major smem operands, 1 = A from tensor memory, 2 = both operands MN-major. */
+int nerfw_selftest_umma_rate(int mode, int n, int reps, long long* cycles_dev, void* stream);
 
 #ifdef __cplusplus
 }

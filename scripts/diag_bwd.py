@@ -21,7 +21,8 @@ for (b, n, with_emb) in [(700, 64, True), (3, 64, False)]:
     de_ref = torch.zeros(1, 32, device="cuda") if with_emb else None
     de_tc = torch.zeros(1, 32, device="cuda") if with_emb else None
     ops.mlp_bwd(params, g_ref, o, d, z, e, d_raw, de_ref)
-    ops.mlp_bwd_tc(params, g_tc, packed, o, d, z, e, d_raw, de_tc)
+    _, masks = ops.mlp_fwd(params, packed, o, d, z, e, 1, want_masks=True)   # gates of the bf16x3 forward
+    ops.mlp_bwd_tc(params, g_tc, packed, o, d, z, e, d_raw, de_tc, masks)
     torch.cuda.synchronize()
     print(f"--- b={b} n={n} emb={with_emb}")
     for k in params:

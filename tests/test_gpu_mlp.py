@@ -174,11 +174,9 @@ def test_mlp_backward_vs_oracle_autograd(cuda_model, oracle, state_dict):
 @pytest.mark.parametrize("with_emb", [True, False])
 @pytest.mark.parametrize("b,n", [(3, 64), (61, 192), (700, 64)])
 def test_tensor_core_backward_vs_fp32_backward(cuda_model, b, n, with_emb):
-    """tcgen05 backward (bf16 operands, fp32 accumulate) against the fp32 CUDA-core backward on the same inputs and the
-    same cotangent.  Stated bf16 bounds: cosine >= 0.99 per tensor and max deviation <= 0.3 of the tensor's max-abs gradient
-    (the deviation is dominated by ReLU-mask flips of near-zero activations between the bf16 and fp32 forward passes:
-    a fraction f of flipped gates moves the gradient by ~sqrt(f), compounding per layer; measured 0.993 at layer 0),
-    heads and appearance branch <= 1e-2."""
+    """tcgen05 backward (bf16 operands, fp32 accumulate, ReLU gates taken from the bf16x3 forward) against the fp32
+    CUDA-core backward on the same inputs and cotangent.  Stated bf16 bounds: every parameter gradient within 3e-2 of
+    that tensor's max-abs gradient and cosine >= 0.9999 (measured 1.5e-2 / 0.99996)."""
     from nerfw import ops
     model, emb = cuda_model
     gen = torch.Generator(device="cuda").manual_seed(b * 13 + n)
@@ -195,7 +193,8 @@ def test_tensor_core_backward_vs_fp32_backward(cuda_model, b, n, with_emb):
     de_ref = torch.zeros(1, 32, device="cuda") if with_emb else None
     de_tc = torch.zeros(1, 32, device="cuda") if with_emb else None
     ops.mlp_bwd(params, g_ref, o, d, z, e, d_raw, de_ref)
-    ops.mlp_bwd_tc(params, g_tc, packed, o, d, z, e, d_raw, de_tc)
+    _, masks = ops.mlp_fwd(params, packed, o, d, z, e, 1, want_masks=True)   # ReLU gates of the bf16x3 forward
+    ops.mlp_bwd_tc(params, g_tc, packed, o, d, z, e, d_raw, de_tc, masks)
     worst, worst_cos = 0.0, 1.0
     for k in params:
         if not with_emb and k.startswith("appearance"):
@@ -205,11 +204,35 @@ def test_tensor_core_backward_vs_fp32_backward(cuda_model, b, n, with_emb):
         rel = float((ref - got).abs().max() / (ref.abs().max() + 1e-20))
         cos = float((ref * got).sum() / (ref.norm() * got.norm() + 1e-30))
         worst, worst_cos = max(worst, rel), min(worst_cos, cos)
-        if k.startswith(("pts_linears", "dir_linear")):
-            assert rel <= 0.3 and cos >= 0.99, (k, rel, cos)
-        else:
-            assert rel <= 1e-2 and cos >= 0.9999, (k, rel, cos)
+        assert rel <= 3e-2 and cos >= 0.9999, (k, rel, cos)
     if with_emb:
         rel = float((de_ref - de_tc).abs().max() / (de_ref.abs().max() + 1e-20))
         assert rel <= 1e-2, rel
     record(f"mlp_bwd_tc_{b}x{n}_{'emb' if with_emb else 'noemb'}", worst_rel=worst, worst_cos=worst_cos)
+
+
+def test_tensor_core_backward_without_forward_gates(cuda_model):
+    """relu_masks = NULL: the backward gates with its own bf16 recompute.  Near-zero activations then gate differently
+    from the fp32 reference (a fraction f of flipped gates moves the gradient by ~sqrt(f) per layer), so only the looser
+    bound cos >= 0.99 holds -- which is why the autograd path always passes the forward's gates."""
+    from nerfw import ops
+    model, emb = cuda_model
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    b, n = 300, 64
+    o = torch.randn(b, 3, device="cuda", generator=gen)
+    d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda", generator=gen), dim=-1)
+    z = torch.sort(torch.rand(b, n, device="cuda", generator=gen) * 4 + 2, dim=-1).values
+    d_raw = torch.randn(b * n, 4, device="cuda", generator=gen)
+    names, tensors = model.kernel_params()
+    params = {k: t.detach() for k, t in zip(names, tensors)}
+    packed = model.packed_weights(names, tensors)
+    g_ref = {k: torch.zeros_like(t) for k, t in params.items()}
+    g_tc = {k: torch.zeros_like(t) for k, t in params.items()}
+    ops.mlp_bwd(params, g_ref, o, d, z, None, d_raw, None)
+    ops.mlp_bwd_tc(params, g_tc, packed, o, d, z, None, d_raw, None, None)
+    for k in params:
+        if k.startswith("appearance"):
+            continue
+        ref, got = g_ref[k].double(), g_tc[k].double()
+        cos = float((ref * got).sum() / (ref.norm() * got.norm() + 1e-30))
+        assert cos >= 0.99, (k, cos)

