@@ -225,43 +225,21 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t s = tile * TM + row;
       const bool live = s < n_total;
-      // ---- encodings.  ch 0: x and position levels 0..6;  ch 1: position levels 7..9 and the direction encoding ----
+      // ---- encodings: ch 0 -> position features 0..31 and the direction tile, ch 1 -> position features 32..63 ----
       {
         float x[3] = {0.f, 0.f, 0.f};
         if (live) src.position(s, x);
+        float v[32];
         if (ch == 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) put_enc<X3>(pex_hi, pex_lo, row, c, x[c]);
-        } else {
-          put_enc<X3>(pex_hi, pex_lo, row, 63, 0.f);
-        }
-        const int l0 = ch == 0 ? 0 : 7, l1 = ch == 0 ? 7 : NERFW_POS_LEVELS;
-        for (int l = l0; l < l1; ++l) {
-          float f = (float)(1u << l);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float sn, cs;
-            sincosf(f * x[c], &sn, &cs);
-            put_enc<X3>(pex_hi, pex_lo, row, 3 + 6 * l + c, sn);
-            put_enc<X3>(pex_hi, pex_lo, row, 6 + 6 * l + c, cs);
-          }
-        }
-        if (ch == 1) {
+          pos_features32<0, !X3>(x, v);
+          store_features32<X3>(pex_hi, pex_lo, row, 0, v);
           float d[3] = {0.f, 0.f, 0.f};
           if (live) src.direction(s, d);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) put_enc<X3>(ped_hi, ped_lo, row, c, d[c]);
-          for (int l = 0; l < NERFW_DIR_LEVELS; ++l) {
-            float f = (float)(1u << l);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float sn, cs;
-              sincosf(f * d[c], &sn, &cs);
-              put_enc<X3>(ped_hi, ped_lo, row, 3 + 6 * l + c, sn);
-              put_enc<X3>(ped_hi, ped_lo, row, 6 + 6 * l + c, cs);
-            }
-          }
-          for (int k = NERFW_DIR_DIM; k < 32; ++k) put_enc<X3>(ped_hi, ped_lo, row, k, 0.f);
+          dir_features32<!X3>(d, v);
+          store_features32<X3>(ped_hi, ped_lo, row, 0, v);
+        } else {
+          pos_features32<1, !X3>(x, v);
+          store_features32<X3>(pex_hi, pex_lo, row, 32, v);
         }
       }
       fence_proxy_async_smem();
@@ -280,32 +258,60 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
           uint32_t r[32];
           tmem_ld32(tlane + COL_ACC + col, r);
           tmem_wait_ld();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bias[col + j], 0.f);
-          if (masks) {  // ReLU gates for the backward pass (training): bit j <-> column col + j
-            uint32_t bits = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-            masks[mask_index(tile, layer, row, ch, q)] = bits;
-          }
-          if (layer == NERFW_LAYERS - 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sig = fmaf(v[j], vec[V_DENW + col + j], sig);
-          }
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col);
           uint32_t ph[16];
+          const bool plain = !X3 && !masks && layer != NERFW_LAYERS - 1;  // warp-uniform
+          if (plain) {
+            // bf16 fast path: one FADD2 + one F2FP.RELU per two columns
 #pragma unroll
-          for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          tmem_st16(tlane + COL_AHI + (col >> 1), ph);
-          if (X3) {
-            uint32_t pl[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float l0v = v[2 * j] - __uint_as_float(ph[j] << 16);
-              float l1v = v[2 * j + 1] - __uint_as_float(ph[j] & 0xffff0000u);
-              pl[j] = pack_bf16x2(l0v, l1v);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              float a0, a1, a2, a3;
+              unpack2f(add2(pack2(r[4 * j4], r[4 * j4 + 1]), pack2f(bb.x, bb.y)), a0, a1);
+              unpack2f(add2(pack2(r[4 * j4 + 2], r[4 * j4 + 3]), pack2f(bb.z, bb.w)), a2, a3);
+              ph[2 * j4] = relu_pack_bf16x2(a0, a1);
+              ph[2 * j4 + 1] = relu_pack_bf16x2(a2, a3);
             }
-            tmem_st16(tlane + COL_ALO + (col >> 1), pl);
+            tmem_st16(tlane + COL_AHI + (col >> 1), ph);
+          } else {
+            float v[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              float a0, a1, a2, a3;
+              unpack2f(add2(pack2(r[4 * j4], r[4 * j4 + 1]), pack2f(bb.x, bb.y)), a0, a1);
+              unpack2f(add2(pack2(r[4 * j4 + 2], r[4 * j4 + 3]), pack2f(bb.z, bb.w)), a2, a3);
+              v[4 * j4] = fmaxf(a0, 0.f); v[4 * j4 + 1] = fmaxf(a1, 0.f);
+              v[4 * j4 + 2] = fmaxf(a2, 0.f); v[4 * j4 + 3] = fmaxf(a3, 0.f);
+            }
+            if (masks) {  // ReLU gates for the backward pass (training): bit j <-> column col + j
+              uint32_t bits = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+              masks[mask_index(tile, layer, row, ch, q)] = bits;
+            }
+            if (layer == NERFW_LAYERS - 1) {
+              const float4* w4 = reinterpret_cast<const float4*>(vec + V_DENW + col);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 ww = w4[j4];
+                sig = fmaf(v[4 * j4], ww.x, sig); sig = fmaf(v[4 * j4 + 1], ww.y, sig);
+                sig = fmaf(v[4 * j4 + 2], ww.z, sig); sig = fmaf(v[4 * j4 + 3], ww.w, sig);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            tmem_st16(tlane + COL_AHI + (col >> 1), ph);
+            if (X3) {
+              uint32_t pl[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float l0v, l1v;
+                unpack2f(sub2(pack2f(v[2 * j], v[2 * j + 1]), pack2(ph[j] << 16, ph[j] & 0xffff0000u)), l0v, l1v);
+                pl[j] = pack_bf16x2(l0v, l1v);
+              }
+              tmem_st16(tlane + COL_ALO + (col >> 1), pl);
+            }
           }
         }
         tmem_wait_st();
@@ -325,7 +331,6 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
         uint32_t r[32];
         tmem_ld32(tlane + COL_ACC + col, r);
         tmem_wait_ld();
-#pragma unroll
         uint32_t bits = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {

@@ -217,43 +217,21 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
       const int64_t s = tile * TM + row;
       const bool live = s < n_total;
       uint8_t* tsc = scratch + (size_t)tile * TILE_BYTES;
-      // ---- encodings (as in the forward kernel) ----
+      // ---- encodings (as in the bf16 forward kernel) ----
       {
         float x[3] = {0.f, 0.f, 0.f};
         if (live) src.position(s, x);
+        float v[32];
         if (ch == 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) put_enc<false>(pex, pex, row, c, x[c]);
-        } else {
-          put_enc<false>(pex, pex, row, 63, 0.f);
-        }
-        const int l0 = ch == 0 ? 0 : 7, l1 = ch == 0 ? 7 : NERFW_POS_LEVELS;
-        for (int l = l0; l < l1; ++l) {
-          float f = (float)(1u << l);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float sn, cs;
-            sincosf(f * x[c], &sn, &cs);
-            put_enc<false>(pex, pex, row, 3 + 6 * l + c, sn);
-            put_enc<false>(pex, pex, row, 6 + 6 * l + c, cs);
-          }
-        }
-        if (ch == 1) {
+          pos_features32<0, true>(x, v);
+          store_features32<false>(pex, pex, row, 0, v);
           float d[3] = {0.f, 0.f, 0.f};
           if (live) src.direction(s, d);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) put_enc<false>(ped, ped, row, c, d[c]);
-          for (int l = 0; l < NERFW_DIR_LEVELS; ++l) {
-            float f = (float)(1u << l);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float sn, cs;
-              sincosf(f * d[c], &sn, &cs);
-              put_enc<false>(ped, ped, row, 3 + 6 * l + c, sn);
-              put_enc<false>(ped, ped, row, 6 + 6 * l + c, cs);
-            }
-          }
-          for (int k = NERFW_DIR_DIM; k < 32; ++k) put_enc<false>(ped, ped, row, k, 0.f);
+          dir_features32<true>(d, v);
+          store_features32<false>(ped, ped, row, 0, v);
+        } else {
+          pos_features32<1, true>(x, v);
+          store_features32<false>(pex, pex, row, 32, v);
         }
       }
       fence_proxy_async_smem();

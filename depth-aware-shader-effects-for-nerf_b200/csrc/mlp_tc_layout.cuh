@@ -86,6 +86,128 @@ __device__ __forceinline__ void put_enc(uint8_t* tile_hi, uint8_t* tile_lo, uint
   if (X3) *reinterpret_cast<__nv_bfloat16*>(tile_lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2) and fused ReLU + bf16x2 conversion ------------------------
+__device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) { return pack2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
+  uint32_t a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+  lo = __uint_as_float(a);
+  hi = __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// {bf16(max(lo_elem,0)), bf16(max(hi_elem,0))} packed, lo_elem in the low half (one F2FP.RELU)
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+
+// ---- positional encodings of one sample row, 32 consecutive features at a time (src/models.py:35-44) ---------------
+// Feature k of the 64-wide position tile: k < 3: x_k; k = 3 + 6 l + c: sin(2^l x_c); k = 6 + 6 l + c: cos(2^l x_c); 63: 0.
+// FAST (bf16 mode): level 0 by sincosf, higher levels by angle doubling (abs. error ~2^l ulp <= 1e-4, far below the bf16
+// rounding of the operand); otherwise every level by sincosf on the exactly scaled argument, like the reference.
+template <int HALF, bool FAST>
+__device__ __forceinline__ void pos_features32(const float (&x)[3], float (&v)[32]) {
+  constexpr int K0 = 32 * HALF;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  if (HALF == 0) { v[0] = x[0]; v[1] = x[1]; v[2] = x[2]; }
+  float sn[3], cs[3];
+#pragma unroll
+  for (int l = 0; l < NERFW_POS_LEVELS; ++l) {
+    const bool needed = (8 + 6 * l >= K0) && (3 + 6 * l < K0 + 32);
+    if (FAST) {
+      if (l == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sincosf(x[c], &sn[c], &cs[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float s2 = 2.0f * sn[c] * cs[c];
+          cs[c] = fmaf(-2.0f * sn[c], sn[c], 1.0f);
+          sn[c] = s2;
+        }
+      }
+    } else if (needed) {
+      const float f = (float)(1u << l);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sincosf(f * x[c], &sn[c], &cs[c]);
+    }
+    if (needed) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int ks = 3 + 6 * l + c - K0, kc = 6 + 6 * l + c - K0;
+        if (ks >= 0 && ks < 32) v[ks] = sn[c];
+        if (kc >= 0 && kc < 32) v[kc] = cs[c];
+      }
+    }
+  }
+}
+// direction tile: 27 features, zero padded to 32
+template <bool FAST>
+__device__ __forceinline__ void dir_features32(const float (&d)[3], float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  v[0] = d[0]; v[1] = d[1]; v[2] = d[2];
+  float sn[3], cs[3];
+#pragma unroll
+  for (int l = 0; l < NERFW_DIR_LEVELS; ++l) {
+    if (FAST && l > 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float s2 = 2.0f * sn[c] * cs[c];
+        cs[c] = fmaf(-2.0f * sn[c], sn[c], 1.0f);
+        sn[c] = s2;
+      }
+    } else {
+      const float f = (float)(1u << l);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sincosf(f * d[c], &sn[c], &cs[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[3 + 6 * l + c] = sn[c];
+      v[6 + 6 * l + c] = cs[c];
+    }
+  }
+}
+// 32 features of one row -> K-major swizzled operand tile(s): four 16-byte stores per copy
+template <bool X3>
+__device__ __forceinline__ void store_features32(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t row, uint32_t k0, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[8 * c + 2 * j], b = v[8 * c + 2 * j + 1];
+      h[j] = pack_bf16x2(a, b);
+      if (X3) l[j] = pack_bf16x2(a - __uint_as_float(h[j] << 16), b - __uint_as_float(h[j] & 0xffff0000u));
+    }
+    const uint32_t off = sw128_offset(row, k0 + 8 * c);
+    *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (X3) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // ReLU gate words written by the forward kernel in training mode and read by the backward kernel:
 // [tile][layer 0..8][row][column half][4 words of 32 gates]; layer 8 = direction layer (2 words per half used).
 constexpr size_t MASK_WORDS_PER_TILE = 9ull * TM * 8;
