@@ -226,7 +226,7 @@ def bench_train_step(nerfw, sd, dev, world, mode, n_rays=4096, steps=6, warmup=2
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1) / steps, world)
     return {"ms_per_step": ms, "rays_per_gpu": n_rays, "n_gpus": world, "samples": "64+128 (coarse+fine fwd/bwd) + Adam",
-            "forward_mode": mode, "backward": "fp32 CUDA-core MLP backward (recompute), composite_bwd",
+            "forward_mode": mode, "backward": "tcgen05 bf16 MLP backward (dgrad fused with forward recompute + MN-major wgrad), composite_bwd",
             "allreduce_bytes": int(tr.flat.grad.numel() * 4) if world > 1 else 0, "final_loss": float(loss)}
 
 

@@ -98,8 +98,16 @@ __global__ void __launch_bounds__(128) app_offset_kernel(NerfwWeights w, const f
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Forward kernel warp roles: 16 epilogue warps (lane quadrant = warp % 4, column quarter = warp / 4: four resident
+// warps per scheduler hide the TMEM / shared-memory latencies of the epilogue), one producer warp, one MMA warp.
+constexpr int F_EPI_WARPS = 16;
+constexpr int F_PRODUCER_WARP = 16;
+constexpr int F_MMA_WARP = 17;
+constexpr int F_THREADS = 576;
+constexpr int F_EPI_THREADS = F_EPI_WARPS * 32;
+
 template <bool X3>
-__global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* __restrict__ packed, SampleSource src,
+__global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* __restrict__ packed, SampleSource src,
                                                                  const float4* __restrict__ app_off, int64_t n_total,
                                                                  float4* __restrict__ raw, uint32_t* __restrict__ masks) {
   extern __shared__ uint8_t smem_dyn[];
@@ -114,16 +122,16 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
   float* sig_part = reinterpret_cast<float*>(sm + SM_SIG);
   float4* rgb_part = reinterpret_cast<float4*>(sm + SM_RGB);
 
-  if (warp == PRODUCER_WARP && lane == 0) {
+  if (warp == F_PRODUCER_WARP && lane == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(a_ready, EPI_THREADS);
+    mbar_init(a_ready, F_EPI_THREADS);
     fence_mbar_init();
   }
-  if (warp == MMA_WARP) tmem_alloc<512>(tmem_ptr);
-  if (warp < EPI_WARPS) {
+  if (warp == F_MMA_WARP) tmem_alloc<512>(tmem_ptr);
+  if (warp < F_EPI_WARPS) {
     const float* gv = reinterpret_cast<const float*>(packed + W_BYTES);
-    for (int i = tid; i < V_FLOATS; i += EPI_THREADS) vec[i] = __ldg(gv + i);
+    for (int i = tid; i < V_FLOATS; i += F_EPI_THREADS) vec[i] = __ldg(gv + i);
   }
   tc_fence_before();
   __syncthreads();
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
   const uint32_t tmem = *tmem_ptr;
   const int64_t ntiles = (n_total + TM - 1) / TM;
 
-  if (warp == PRODUCER_WARP) {
+  if (warp == F_PRODUCER_WARP) {
     // ===================== weight producer =====================
     if (lane == 0) {
       Pipe p;
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
         }
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == F_MMA_WARP) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       Pipe p;
@@ -213,8 +221,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
       }
     }
   } else {
-    // ===================== encoders + epilogues (8 warps, thread <-> sample row) =====================
-    const uint32_t quad = warp & 3, ch = warp >> 2;
+    // ===================== encoders + epilogues (16 warps, thread <-> sample row x column quarter) ==========
+    const uint32_t quad = warp & 3, cq = warp >> 2;
     const uint32_t row = quad * 32 + lane;
     const uint32_t tlane = tmem + ((quad * 32) << 16);
     uint32_t acc_phase = 0;
@@ -225,21 +233,22 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t s = tile * TM + row;
       const bool live = s < n_total;
-      // ---- encodings: ch 0 -> position features 0..31 and the direction tile, ch 1 -> position features 32..63 ----
+      // ---- encodings: quarter 0 / 1 -> position features 0..31 / 32..63, quarter 2 -> the direction tile ----
       {
         float x[3] = {0.f, 0.f, 0.f};
         if (live) src.position(s, x);
         float v[32];
-        if (ch == 0) {
+        if (cq == 0) {
           pos_features32<0, !X3>(x, v);
           store_features32<X3>(pex_hi, pex_lo, row, 0, v);
+        } else if (cq == 1) {
+          pos_features32<1, !X3>(x, v);
+          store_features32<X3>(pex_hi, pex_lo, row, 32, v);
+        } else if (cq == 2) {
           float d[3] = {0.f, 0.f, 0.f};
           if (live) src.direction(s, d);
           dir_features32<!X3>(d, v);
           store_features32<X3>(ped_hi, ped_lo, row, 0, v);
-        } else {
-          pos_features32<1, !X3>(x, v);
-          store_features32<X3>(pex_hi, pex_lo, row, 32, v);
         }
       }
       fence_proxy_async_smem();
@@ -253,8 +262,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
         tc_fence_after();
         const float* bias = vec + V_PTSB + layer * 256;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t col = ch * 128 + q * 32;
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t col = cq * 64 + q * 32;
           uint32_t r[32];
           tmem_ld32(tlane + COL_ACC + col, r);
           tmem_wait_ld();
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
               uint32_t bits = 0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-              masks[mask_index(tile, layer, row, ch, q)] = bits;
+              masks[mask_index(tile, layer, row, 0, (int)(col >> 5))] = bits;
             }
             if (layer == NERFW_LAYERS - 1) {
               const float4* w4 = reinterpret_cast<const float4*>(vec + V_DENW + col);
@@ -318,16 +327,15 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
         tc_fence_before();
         mbar_arrive(a_ready);
       }
-      sig_part[ch * TM + row] = sig;
+      sig_part[cq * TM + row] = sig;
 
       // ---- direction-layer epilogue + rgb head (src/models.py:141-160) ----
       mbar_wait(acc_full, acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
       float p3[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int q = 0; q < 2; ++q) {
-        const uint32_t col = ch * 64 + q * 32;
+      {
+        const uint32_t col = cq * 32;
         uint32_t r[32];
         tmem_ld32(tlane + COL_ACC + col, r);
         tmem_wait_ld();
@@ -339,20 +347,20 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
 #pragma unroll
           for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv, vec[V_RGBW + c * 128 + col + j], p3[c]);
         }
-        if (masks) masks[mask_index(tile, NERFW_LAYERS, row, ch, q)] = bits;
+        if (masks) masks[mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))] = bits;
       }
       tc_fence_before();
-      if (ch == 1) rgb_part[row] = make_float4(p3[0], p3[1], p3[2], 0.f);
-      named_bar_sync(1, EPI_THREADS);
-      if (ch == 0 && live) {
-        float4 other = rgb_part[row];
+      if (cq != 0) rgb_part[cq * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
+      named_bar_sync(1, F_EPI_THREADS);
+      if (cq == 0 && live) {
+        const float4 o1 = rgb_part[TM + row], o2 = rgb_part[2 * TM + row], o3 = rgb_part[3 * TM + row];
         float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
         if (app_off) off = __ldg(app_off + src.emb_row(s));
-        float sg = sig_part[row] + sig_part[TM + row] + vec[V_DENB];
+        float sg = (sig_part[row] + sig_part[TM + row]) + (sig_part[2 * TM + row] + sig_part[3 * TM + row]) + vec[V_DENB];
         float4 o;
-        o.x = 1.0f / (1.0f + expf(-(p3[0] + other.x + vec[V_RGBB + 0] + off.x)));
-        o.y = 1.0f / (1.0f + expf(-(p3[1] + other.y + vec[V_RGBB + 1] + off.y)));
-        o.z = 1.0f / (1.0f + expf(-(p3[2] + other.z + vec[V_RGBB + 2] + off.z)));
+        o.x = 1.0f / (1.0f + expf(-(p3[0] + o1.x + o2.x + o3.x + vec[V_RGBB + 0] + off.x)));
+        o.y = 1.0f / (1.0f + expf(-(p3[1] + o1.y + o2.y + o3.y + vec[V_RGBB + 1] + off.y)));
+        o.z = 1.0f / (1.0f + expf(-(p3[2] + o1.z + o2.z + o3.z + vec[V_RGBB + 2] + off.z)));
         o.w = fmaxf(sg, 0.f);
         raw[s] = o;
       }
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* _
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == F_MMA_WARP) {
     __syncwarp();
     tmem_dealloc<512>(tmem);
   }
@@ -473,9 +481,9 @@ int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSou
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   const float4* ao = reinterpret_cast<const float4*>(app_off);
   if (x3)
-    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks));
+    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks));
   else
-    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks));
+    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks));
   NERFW_LAUNCHED();
   return NERFW_OK;
 }

@@ -46,9 +46,9 @@ constexpr uint32_t SM_PED_HI = 32768;
 constexpr uint32_t SM_PED_LO = 49152;
 constexpr uint32_t SM_RING = 65536;
 constexpr uint32_t SM_VEC = SM_RING + NSTAGES * BIG_CHUNK;        // 196608
-constexpr uint32_t SM_SIG = SM_VEC + V_FLOATS * 4;                // [2][128] floats
-constexpr uint32_t SM_RGB = SM_SIG + 2 * TM * 4;                  // [128] float4
-constexpr uint32_t SM_BAR = SM_RGB + TM * 16;                     // full[4], empty[4], acc_full, a_ready
+constexpr uint32_t SM_SIG = SM_VEC + V_FLOATS * 4;                // [4][128] floats (density partial sums)
+constexpr uint32_t SM_RGB = SM_SIG + 4 * TM * 4;                  // [4][128] float4 (rgb logit partial sums)
+constexpr uint32_t SM_BAR = SM_RGB + 4 * TM * 16;                     // full[4], empty[4], acc_full, a_ready
 constexpr uint32_t SM_TMEMPTR = SM_BAR + (2 * NSTAGES + 2) * 8;
 constexpr uint32_t SM_TOTAL = SM_TMEMPTR + 16;
 constexpr size_t SMEM_BYTES = SM_TOTAL + 1024;  // slack for the manual 1024-byte alignment
