@@ -326,7 +326,10 @@ def run_ours(args):
             flops = FLOP_PER_SAMPLE * float(z_fine.numel())
             ach = flops / (kms * 1e-3) / 1e12
             roof[m] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                       "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                       "frac": ach / peaks["bf16_tflops_sustained"],
+                       # DRAM bytes per launch: 18.9 B/sample measured by ncu --set full on a 160k-ray crop
+                       # (profiles/r01_ncu_full_*.md: 141 MB read + 439 MB written for 30.7 M samples) x samples here
+                       "traffic": 18.9 * float(z_fine.numel()),
                        "kernel": "mlp_tc_fwd_kernel" if m != "fp32" else "mlp_ffma_fwd_kernel",
                        "kernel_ms": kms, "samples_per_launch": int(z_fine.numel()),
                        "peak_source": f"bf16 dense sustained, {peaks['source']}",
@@ -376,6 +379,22 @@ def run_ours(args):
             barrier(world)
         ms = max_over_ranks(a0.elapsed_time(a1) / 2, world)
         other_modes[m] = {"value": world * n_rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms}
+    # the reference's own calling pattern: 4096-ray chunks with a device->host copy per chunk
+    # (render_aligned_spiral.py:136-155), one frame
+    with torch.no_grad():
+        barrier(world)
+        t0 = time.perf_counter()
+        parts = []
+        for j in range(0, n_rays, 4096):
+            c_rgb, c_depth, _ = nerfw.volume_render(model, o_dev[j:j + 4096], d_dev[j:j + 4096], NEAR, FAR, N_COARSE,
+                                                    N_IMPORTANCE, appearance_embedding=emb_d, perturb=False,
+                                                    mlp_dtype=mode, generator=gen)
+            parts.append((c_rgb.cpu(), c_depth.cpu()))
+        barrier(world)
+        chunk_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world)
+    other_modes["chunked_4096_with_cpu_copy"] = {"value": world * n_rays / (chunk_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                                                 "ms_per_step": chunk_ms, "mlp_mode": mode,
+                                                 "calls_per_frame": (n_rays + 4095) // 4096}
     train = bench_train_step(nerfw, sd, dev, world, mode)
 
     if rank != 0:

@@ -180,3 +180,48 @@ def test_render_frame_matches_chunked_reference_pattern(cuda_model, oracle):
     assert np.array_equal(depth8.cpu().numpy(), ((dn - dn.min()) / (dn.max() - dn.min()) * 255).astype(np.uint8))
     frames = list(render_path(model, aligned_spiral_poses(3, 1), 16, 16, blender_focal(16), 2.0, 6.0, 16, 16, appearance_embedding=emb))
     assert [f[0] for f in frames] == [0, 1, 2] and frames[0][1].shape == (16, 16, 3) and frames[0][1].dtype == np.uint8
+
+
+def test_ray_bank_checkpoint_and_fog(cuda_model, oracle, tmp_path):
+    """Rows N2-N4 of SURVEY.md section 8f: device ray bank == per-image get_rays; checkpoint schema round trip with the
+    reference's keys; fog on float buffers == the reference's numpy formula (src/post_processor.py:451-493)."""
+    import nerfw
+    from nerfw.checkpoint import load_checkpoint, save_checkpoint
+    from nerfw.effects import fog
+    from nerfw.raybank import RayBank
+    from nerfw.camera import aligned_spiral_poses, blender_focal
+    from config import Config
+    model, emb = cuda_model
+    poses = torch.from_numpy(aligned_spiral_poses(3, 1))
+    imgs = torch.rand(3, 20, 24, 4)
+    focal = blender_focal(24)
+    bank = RayBank(imgs, poses, focal)
+    _, want = oracle.rays_for_view(20, 24, focal, poses[1])
+    full = bank.image_rays(1)
+    assert torch.equal(full["rays_d"].cpu(), want.reshape(-1, 3)) and full["rgb"].shape == (480, 3)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    b = bank.sample(100, generator=g)
+    assert b["rays_d"].shape == (100, 3) and b["rgb"].shape == (100, 3) and b["alpha"].shape == (100, 1)
+    assert 0 <= b["img_idx"] < 3 and torch.equal(b["rays_o"][0].cpu(), poses[b["img_idx"], :3, 3])
+    # checkpoint
+    table = torch.nn.Parameter(torch.randn(3, 32))
+    path = save_checkpoint(str(tmp_path), 1000, model, table, loss=0.5, psnr=3.0)
+    assert path.endswith("checkpoint_001000.pt")
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"model_state_dict", "optimizer_state_dict", "loss", "psnr", "iteration", "appearance_embeddings"}
+    m2 = nerfw.NeRF(Config())
+    t2 = torch.nn.Parameter(torch.zeros(3, 32))
+    load_checkpoint(path, m2, t2)
+    assert all(torch.equal(a.cpu(), b_) for a, b_ in zip(model.state_dict().values(), m2.state_dict().values()))
+    assert torch.equal(t2.data, table.data)
+    # fog
+    rgb = torch.rand(16, 16, 3, device="cuda")
+    depth = torch.rand(16, 16, device="cuda") * 4 + 2
+    got = fog(rgb, depth).cpu().numpy()
+    img8 = (rgb.cpu() * 255).numpy().astype(np.uint8)
+    dn = depth.cpu().numpy()
+    dn = dn / dn.max()
+    adj = np.clip(np.maximum(dn - 0.0, 0.0) / 1.0, 0.0, 1.0) ** 3.0 * 0.3
+    f3 = np.stack([adj] * 3, axis=2)
+    ref = np.clip(img8.astype(np.float32) * f3 + np.array([255, 255, 255], np.float32) * (1.0 - f3), 0, 255).astype(np.uint8)
+    assert int(np.abs(got.astype(int) - ref.astype(int)).max()) <= 1   # fp32 pow on device vs numpy float64 promotion
