@@ -225,3 +225,25 @@ def test_ray_bank_checkpoint_and_fog(cuda_model, oracle, tmp_path):
     f3 = np.stack([adj] * 3, axis=2)
     ref = np.clip(img8.astype(np.float32) * f3 + np.array([255, 255, 255], np.float32) * (1.0 - f3), 0, 255).astype(np.uint8)
     assert int(np.abs(got.astype(int) - ref.astype(int)).max()) <= 1   # fp32 pow on device vs numpy float64 promotion
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_high_sample_stress_config(cuda_model, oracle, state_dict, mode):
+    """BASELINE.json configs[4]: 256 + 512 samples (fine pass on 768), depth output, vs the composed oracle on 48 rays."""
+    import nerfw
+    model, emb = cuda_model
+    sd, emb_cpu = state_dict
+    o, d = view(oracle)
+    sel = torch.arange(0, 10000, 209, device="cuda")[:48]
+    oc, dc = o.reshape(-1, 3)[sel].contiguous(), d.reshape(-1, 3)[sel].contiguous()
+    torch.manual_seed(17)
+    u = torch.rand(48, 512)
+    with torch.no_grad():
+        rgb_o, depth_o, ex_o = oracle.render_hier(sd, sd, oc.cpu(), dc.cpu(), 2.0, 6.0, 256, 512, emb=emb_cpu, perturb=False, u_rand=u)
+        rgb, depth, ex = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 256, 512, appearance_embedding=emb, perturb=False,
+                                             mlp_dtype=mode, u_rand=u)
+    assert ex["z_vals"].shape == (48, 768)
+    e = dict(rgb=maxabs(rgb, rgb_o), depth=maxabs(depth, depth_o), acc=maxabs(ex["acc"], ex_o["acc"]))
+    record(f"stress_256_512_{mode}", **e)
+    t = TOL[mode]
+    assert e["rgb"] <= t[0] and e["depth"] <= t[1] and e["acc"] <= t[2], e
