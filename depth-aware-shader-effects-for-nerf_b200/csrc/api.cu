@@ -27,6 +27,13 @@ int sm_count() {
   }
   return cached;
 }
+bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  if (mask & (1ull << dev)) return false;
+  mask |= 1ull << dev;
+  return true;
+}
 }  // namespace nerfw
 
 extern "C" {

@@ -41,6 +41,10 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int sm_count();  // cached multiprocessor count of the current device
 
+// True the first time it is called for the current device with this (per call site) mask: function attributes such as the
+// dynamic shared-memory limit are per device, so launchers set them once per device rather than once per process.
+bool first_use_on_device(unsigned long long& mask);
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace nerfw

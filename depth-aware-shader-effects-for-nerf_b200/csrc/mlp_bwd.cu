@@ -402,11 +402,10 @@ extern "C" int nerfw_mlp_bwd(const NerfwWeights* w, const float* pts_or_o, const
   src.emb_shared = (emb_rows == 1) ? 1 : 0;
   const int64_t total = n_rays * (z ? n_samples : 1);
 
-  static thread_local bool attr_set = false;
+  static thread_local unsigned long long attr_mask = 0;
   const size_t smem = sizeof(ffma::BwdSmem);
-  if (!attr_set) {
+  if (first_use_on_device(attr_mask)) {
     NERFW_CUDA(cudaFuncSetAttribute(ffma::mlp_ffma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   int64_t ntiles = ceil_div64(total, ffma::TM);
   int64_t grid = ntiles < sm_count() ? ntiles : sm_count();

@@ -158,11 +158,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_ffma_fwd_kernel(NerfwWeights w
 
 int launch_mlp_ffma_fwd(const NerfwWeights& w, const SampleSource& src, const float* app_off, int64_t n_total, float* raw,
                         cudaStream_t stream) {
-  static thread_local bool attr_set = false;
+  static thread_local unsigned long long attr_mask = 0;
   const size_t smem = sizeof(ffma::Smem);
-  if (!attr_set) {
+  if (first_use_on_device(attr_mask)) {
     NERFW_CUDA(cudaFuncSetAttribute(ffma::mlp_ffma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   int64_t ntiles = ceil_div64(n_total, ffma::TM);
   int64_t grid = ntiles < sm_count() ? ntiles : sm_count();

@@ -3,7 +3,7 @@
 // (src/models.py:35-44).
 //
 // Per CTA (one per SM) and per tile of 128 samples:
-//   * 8 epilogue warps compute the encodings into shared memory (K-major, 128B-swizzled UMMA operand tiles);
+//   * 16 epilogue warps compute the encodings into shared memory (K-major, 128B-swizzled UMMA operand tiles);
 //   * one producer thread streams the pre-swizzled bf16 weight chunks (32 KB = 256 outputs x 64 inputs) from L2 into a
 //     4-stage shared-memory ring with cp.async.bulk (TMA engine) + mbarrier transaction counts;
 //   * one MMA thread issues tcgen05.mma kind::f16 (M=128, N=256|128, K=16) with the accumulator in TMEM columns
@@ -470,11 +470,10 @@ int launch_app_offset(const NerfwWeights& w, const float* emb, int64_t emb_rows,
 int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSource& src, const float* app_off,
                       int64_t n_total, bool x3, float* raw, void* relu_masks, cudaStream_t stream) {
   (void)w;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    attr_set = true;
   }
   int64_t ntiles = ceil_div64(n_total, tc::TM);
   int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
@@ -498,10 +497,9 @@ extern "C" int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n
   NERFW_REQUIRE(k >= 64 && k <= 256 && k % 64 == 0, "nerfw_selftest_umma: K must be a multiple of 64 in [64,256]");
   NERFW_REQUIRE(mode == 0 || mode == 1, "nerfw_selftest_umma: mode must be 0 (SS) or 1 (TS)");
   const size_t smem = 65536 + 131072 + 64 + 1024;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     NERFW_CUDA(cudaFuncSetAttribute(tc::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   tc::umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(a_bf16),
                                                                reinterpret_cast<const __nv_bfloat16*>(b_bf16), n, k, mode, d);

@@ -847,11 +847,10 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   const int64_t ntiles = ceil_div64(total, tc::TM);
   NERFW_REQUIRE(ntiles < (1ll << 30), "nerfw_mlp_bwd_tc: too many samples");
 
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     NERFW_CUDA(cudaFuncSetAttribute(tcb::mlp_tc_bwd_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::SMEM1_BYTES));
     NERFW_CUDA(cudaFuncSetAttribute(tcb::mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::SMEM2_BYTES));
-    attr_set = true;
   }
   const int sms = sm_count();
   int64_t grid1 = ntiles < sms ? ntiles : sms;
@@ -884,7 +883,7 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   plan.d_rgb_w = grads->rgb_w;
   plan.d_rgb_b = grads->rgb_b;
   {
-    const char* dbg = getenv("NERFW_WGRAD_DEBUG");
+    const char* dbg = getenv("NERFW_WGRAD_DEBUG");  // profiling switch (scripts/time_bwd.py); results are wrong when set
     plan.debug = dbg ? atoi(dbg) : 0;
   }
   double cost[13], csum = 0;
@@ -946,10 +945,9 @@ extern "C" int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, 
   NERFW_REQUIRE(n >= 64 && n <= 256 && n % 64 == 0, "nerfw_selftest_umma_mn: N must be a multiple of 64 in [64,256]");
   NERFW_REQUIRE(k >= 16 && k <= 256 && k % 16 == 0, "nerfw_selftest_umma_mn: K must be a multiple of 16 in [16,256]");
   const size_t smem = 65536 + 131072 + 64 + 1024;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     NERFW_CUDA(cudaFuncSetAttribute(tcb::umma_selftest_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   tcb::umma_selftest_mn_kernel<<<1, 128, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(at_bf16),
                                                                     reinterpret_cast<const __nv_bfloat16*>(bt_bf16), n, k, d);
@@ -961,10 +959,9 @@ extern "C" int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, 
 extern "C" int nerfw_selftest_umma_rate(int mode, int n, int reps, long long* cycles_dev, void* stream) {
   NERFW_REQUIRE(cycles_dev && mode >= 0 && mode <= 2 && n >= 16 && n <= 256 && n % 16 == 0 && reps >= 1, "nerfw_selftest_umma_rate: bad arguments");
   const size_t smem = 65536 + 131072 + 64 + 1024;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     NERFW_CUDA(cudaFuncSetAttribute(tcb::umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   tcb::umma_rate_kernel<<<1, 128, smem, as_stream(stream)>>>(mode, n, reps, cycles_dev);
   NERFW_LAUNCHED();

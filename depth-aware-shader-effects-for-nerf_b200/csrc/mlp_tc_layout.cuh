@@ -77,15 +77,6 @@ struct Pipe {
   }
 };
 
-// write one encoded value (hi and optionally lo) into a K-major swizzled operand tile
-template <bool X3>
-__device__ __forceinline__ void put_enc(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t row, uint32_t k, float v) {
-  uint32_t off = sw128_offset(row, k);
-  __nv_bfloat16 h = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(tile_hi + off) = h;
-  if (X3) *reinterpret_cast<__nv_bfloat16*>(tile_lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
-}
-
 // ---- packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2) and fused ReLU + bf16x2 conversion ------------------------
 __device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) {
   uint64_t r;
