@@ -46,7 +46,7 @@ constexpr size_t TILE_BYTES = 71ull * BLK;
 // pass-1 shared memory: forward map, with the *_LO tiles reused for the ReLU masks and two small vectors appended
 constexpr uint32_t SM1_MASK_A = SM_PEX_LO;  // layers 0..3: [layer][row][ch][4 words]
 constexpr uint32_t SM1_MASK_B = SM_PED_LO;  // layers 4..7
-constexpr uint32_t SM1_DSIG = SM_RGB + 2 * TM * 16;  // rgb partial sums of BOTH column halves live at SM_RGB here
+constexpr uint32_t SM1_DSIG = SM_RGB + 4 * TM * 16;  // after the [4][128] float4 rgb partial sums
 constexpr uint32_t SM1_APPV = SM1_DSIG + TM * 4;
 constexpr uint32_t SM1_BAR = SM1_APPV + 128 * 4;
 constexpr uint32_t SM1_TMEMPTR = SM1_BAR + (2 * NSTAGES + 2) * 8;
@@ -75,9 +75,28 @@ __global__ void __launch_bounds__(256) pack_weights_t_kernel(NerfwWeights w, uin
       *reinterpret_cast<const uint4*>(v);
 }
 
-__device__ __forceinline__ uint32_t* mask_words(uint8_t* sm, int layer, uint32_t row, uint32_t ch) {
+// pass-1 warp roles (same split as the forward kernel): 16 epilogue warps, one producer, one MMA issuer
+constexpr int P1_EPI_WARPS = 16;
+constexpr int P1_PRODUCER_WARP = 16;
+constexpr int P1_MMA_WARP = 17;
+constexpr int P1_THREADS = 576;
+constexpr int P1_EPI_THREADS = P1_EPI_WARPS * 32;
+
+// own ReLU gate words (used only when the caller passes no forward masks): [layer][row][8 words], word = column / 32
+__device__ __forceinline__ uint32_t* mask_words(uint8_t* sm, int layer, uint32_t row) {
   uint8_t* base = sm + (layer < 4 ? SM1_MASK_A : SM1_MASK_B);
-  return reinterpret_cast<uint32_t*>(base) + (((layer & 3) * TM + row) * 2 + ch) * 4;
+  return reinterpret_cast<uint32_t*>(base) + ((layer & 3) * TM + row) * 8;
+}
+// 0xffffffff if bit `pos` of x is set, else 0 (one BFE.S32)
+__device__ __forceinline__ uint32_t bit_mask(uint32_t x, int pos) {
+  int r;
+  asm("bfe.s32 %0, %1, %2, 1;" : "=r"(r) : "r"((int)x), "r"(pos));
+  return (uint32_t)r;
+}
+// packed bf16x2 (g_lo, g_hi) gated by bits 2j and 2j+1 of `bits`
+__device__ __forceinline__ uint32_t gate_pack(float g_lo, float g_hi, uint32_t bits, int j) {
+  const uint32_t p = pack_bf16x2(g_lo, g_hi);
+  return p & __byte_perm(bit_mask(bits, 2 * j), bit_mask(bits, 2 * j + 1), 0x5410);
 }
 
 // 32 consecutive features (16 packed bf16x2 words) of one sample row -> scratch block in the swizzled image
@@ -92,7 +111,7 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int block0, uint32_t 
 }
 
 // ====================================================================================================================
-__global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint8_t* __restrict__ packed, SampleSource src,
+__global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint8_t* __restrict__ packed, SampleSource src,
                                                                        const float4* __restrict__ app_off,
                                                                        const float* __restrict__ app_vec,
                                                                        const float4* __restrict__ d_raw, int64_t n_total,
@@ -109,23 +128,23 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM1_TMEMPTR);
   float* vec = reinterpret_cast<float*>(sm + SM_VEC);
   float* sig_part = reinterpret_cast<float*>(sm + SM_SIG);
-  float4* rgb_part = reinterpret_cast<float4*>(sm + SM_RGB);  // [2][128]
+  float4* rgb_part = reinterpret_cast<float4*>(sm + SM_RGB);  // [4][128]
   float* dsig_s = reinterpret_cast<float*>(sm + SM1_DSIG);
   float* appv = reinterpret_cast<float*>(sm + SM1_APPV);
 
-  if (warp == PRODUCER_WARP && lane == 0) {
+  if (warp == P1_PRODUCER_WARP && lane == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(a_ready, EPI_THREADS);
+    mbar_init(a_ready, P1_EPI_THREADS);
     fence_mbar_init();
   }
-  if (warp == MMA_WARP) tmem_alloc<512>(tmem_ptr);
-  if (warp < EPI_WARPS) {
+  if (warp == P1_MMA_WARP) tmem_alloc<512>(tmem_ptr);
+  if (warp < P1_EPI_WARPS) {
     const float* gv = reinterpret_cast<const float*>(packed + W_BYTES);
-    for (int i = tid; i < V_FLOATS; i += EPI_THREADS) vec[i] = __ldg(gv + i);
+    for (int i = tid; i < V_FLOATS; i += P1_EPI_THREADS) vec[i] = __ldg(gv + i);
     if (tid < 128) appv[tid] = app_vec ? __ldg(app_vec + tid) : 0.f;
     // the unused half of the direction-encoding tile must be finite: it is a (discarded) wgrad operand column
-    for (int i = tid; i < 16384 / 16; i += EPI_THREADS) reinterpret_cast<uint4*>(sm + SM_PED_HI)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 16384 / 16; i += P1_EPI_THREADS) reinterpret_cast<uint4*>(sm + SM_PED_HI)[i] = make_uint4(0, 0, 0, 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
   const int64_t ntiles = (n_total + TM - 1) / TM;
   const uint8_t* packed_t = packed + PACKED_T_OFFSET;
 
-  if (warp == PRODUCER_WARP) {
+  if (warp == P1_PRODUCER_WARP) {
     if (lane == 0) {
       Pipe p;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -153,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
         }
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == P1_MMA_WARP) {
     if (lane == 0) {
       Pipe p;
       uint32_t ar_phase = 0;
@@ -207,7 +226,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
       }
     }
   } else {
-    const uint32_t quad = warp & 3, ch = warp >> 2;
+    // ===================== encoders + epilogues: thread <-> (sample row, column quarter) =====================
+    const uint32_t quad = warp & 3, cq = warp >> 2;
     const uint32_t row = quad * 32 + lane;
     const uint32_t tlane = tmem + ((quad * 32) << 16);
     uint32_t acc_phase = 0;
@@ -222,61 +242,82 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
         float x[3] = {0.f, 0.f, 0.f};
         if (live) src.position(s, x);
         float v[32];
-        if (ch == 0) {
+        if (cq == 0) {
           pos_features32<0, true>(x, v);
           store_features32<false>(pex, pex, row, 0, v);
+        } else if (cq == 1) {
+          pos_features32<1, true>(x, v);
+          store_features32<false>(pex, pex, row, 32, v);
+        } else if (cq == 2) {
           float d[3] = {0.f, 0.f, 0.f};
           if (live) src.direction(s, d);
           dir_features32<true>(d, v);
           store_features32<false>(ped, ped, row, 0, v);
-        } else {
-          pos_features32<1, true>(x, v);
-          store_features32<false>(pex, pex, row, 32, v);
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(a_ready);
       // encodings -> scratch (wgrad operands of layer 0, the skip part of layer 4 and the direction layer)
-      named_bar_sync(1, EPI_THREADS);
+      named_bar_sync(1, P1_EPI_THREADS);
       {
-        const int t = warp * 32 + lane;  // 0..255
+        const int t = warp * 32 + lane;  // 0..511
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int o = (t + 256 * i) * 16;
+        for (int i = 0; i < 2; ++i) {
+          const int o = (t + 512 * i) * 16;
           *reinterpret_cast<uint4*>(tsc + (size_t)XB_ENCX * BLK + o) = *reinterpret_cast<const uint4*>(pex + o);
           *reinterpret_cast<uint4*>(tsc + (size_t)XB_ENCD * BLK + o) = *reinterpret_cast<const uint4*>(ped + o);
         }
       }
 
-      // ---- forward trunk epilogues: next A operand, activation tile, ReLU mask ----
+      // ---- forward trunk epilogues: next A operand + activation tile (+ own ReLU gates when none were passed) ----
       float sig = 0.f;
       for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
         const float* bias = vec + V_PTSB + layer * 256;
-        uint32_t* mw = mask_words(sm, layer, row, ch);
+        const bool plain = fwd_masks != nullptr && layer != NERFW_LAYERS - 1;  // warp-uniform
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t col = ch * 128 + q * 32;
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t col = cq * 64 + q * 32;
           uint32_t r[32];
           tmem_ld32(tlane + COL_ACC + col, r);
           tmem_wait_ld();
-          float v[32];
-          uint32_t bits = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = fmaxf(__uint_as_float(r[j]) + bias[col + j], 0.f);
-            bits |= (v[j] > 0.f ? 1u : 0u) << j;
-          }
-          if (!fwd_masks) mw[q] = bits;
-          if (layer == NERFW_LAYERS - 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sig = fmaf(v[j], vec[V_DENW + col + j], sig);
-          }
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col);
           uint32_t ph[16];
+          if (plain) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              float a0, a1, a2, a3;
+              unpack2f(add2(pack2(r[4 * j4], r[4 * j4 + 1]), pack2f(bb.x, bb.y)), a0, a1);
+              unpack2f(add2(pack2(r[4 * j4 + 2], r[4 * j4 + 3]), pack2f(bb.z, bb.w)), a2, a3);
+              ph[2 * j4] = relu_pack_bf16x2(a0, a1);
+              ph[2 * j4 + 1] = relu_pack_bf16x2(a2, a3);
+            }
+          } else {
+            float v[32];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              v[4 * j4] = fmaxf(__uint_as_float(r[4 * j4]) + bb.x, 0.f);
+              v[4 * j4 + 1] = fmaxf(__uint_as_float(r[4 * j4 + 1]) + bb.y, 0.f);
+              v[4 * j4 + 2] = fmaxf(__uint_as_float(r[4 * j4 + 2]) + bb.z, 0.f);
+              v[4 * j4 + 3] = fmaxf(__uint_as_float(r[4 * j4 + 3]) + bb.w, 0.f);
+            }
+            if (!fwd_masks) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+              mask_words(sm, layer, row)[col >> 5] = bits;
+            }
+            if (layer == NERFW_LAYERS - 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sig = fmaf(v[j], vec[V_DENW + col + j], sig);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          }
           tmem_st16(tlane + COL_AHI + (col >> 1), ph);
           store_row32(tsc, XB_H(layer + 1), row, col, ph);
         }
@@ -284,56 +325,56 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
         tc_fence_before();
         mbar_arrive(a_ready);
       }
-      sig_part[ch * TM + row] = sig;
+      sig_part[cq * TM + row] = sig;
 
-      // ---- direction layer epilogue: rgb, d logits, d sigma_pre, dZ of the direction layer ----
+      // ---- direction layer epilogue: rgb, d logits, d sigma_pre, dZ of the direction layer (32 columns per thread) ----
       mbar_wait(acc_full, acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
       float p3[3] = {0.f, 0.f, 0.f};
-      uint32_t hmask[2];
-#pragma unroll 1
-      for (int q = 0; q < 2; ++q) {
-        const uint32_t col = ch * 64 + q * 32;
+      uint32_t hmask;
+      const uint32_t dcol = cq * 32;
+      {
         uint32_t r[32];
-        tmem_ld32(tlane + COL_ACC + col, r);
+        tmem_ld32(tlane + COL_ACC + dcol, r);
         tmem_wait_ld();
         uint32_t bits = 0;
         uint32_t ph[16];
         float hv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          hv[j] = fmaxf(__uint_as_float(r[j]) + vec[V_DIRB + col + j], 0.f);
+          hv[j] = fmaxf(__uint_as_float(r[j]) + vec[V_DIRB + dcol + j], 0.f);
           bits |= (hv[j] > 0.f ? 1u : 0u) << j;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv[j], vec[V_RGBW + c * 128 + col + j], p3[c]);
+          for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv[j], vec[V_RGBW + c * 128 + dcol + j], p3[c]);
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(hv[2 * j] + appv[col + 2 * j], hv[2 * j + 1] + appv[col + 2 * j + 1]);
-        store_row32(tsc, XB_HDT, row, col, ph);
-        hmask[q] = fwd_masks ? __ldg(fwd_masks + mask_index(tile, NERFW_LAYERS, row, ch, q)) : bits;
+        for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(hv[2 * j] + appv[dcol + 2 * j], hv[2 * j + 1] + appv[dcol + 2 * j + 1]);
+        store_row32(tsc, XB_HDT, row, dcol, ph);
+        hmask = fwd_masks ? __ldg(fwd_masks + mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))) : bits;
       }
       tc_fence_before();
-      rgb_part[ch * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
-      named_bar_sync(1, EPI_THREADS);
+      rgb_part[cq * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
+      named_bar_sync(1, P1_EPI_THREADS);
       float dlog[3];
       {
-        const float4 other = rgb_part[(ch ^ 1) * TM + row];
+        const float4 q0 = rgb_part[row], q1 = rgb_part[TM + row], q2 = rgb_part[2 * TM + row], q3 = rgb_part[3 * TM + row];
         float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
         if (app_off && live) off = __ldg(app_off);  // shared embedding only
         float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live) dr = __ldg(d_raw + s);
-        const float lg[3] = {p3[0] + other.x + vec[V_RGBB + 0] + off.x, p3[1] + other.y + vec[V_RGBB + 1] + off.y,
-                             p3[2] + other.z + vec[V_RGBB + 2] + off.z};
+        const float lg[3] = {(q0.x + q1.x) + (q2.x + q3.x) + vec[V_RGBB + 0] + off.x,
+                             (q0.y + q1.y) + (q2.y + q3.y) + vec[V_RGBB + 1] + off.y,
+                             (q0.z + q1.z) + (q2.z + q3.z) + vec[V_RGBB + 2] + off.z};
         const float dd[3] = {dr.x, dr.y, dr.z};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float rgb = 1.0f / (1.0f + expf(-lg[c]));
           dlog[c] = dd[c] * rgb * (1.0f - rgb);
         }
-        const float pre = sig_part[row] + sig_part[TM + row] + vec[V_DENB];
+        const float pre = (sig_part[row] + sig_part[TM + row]) + (sig_part[2 * TM + row] + sig_part[3 * TM + row]) + vec[V_DENB];
         const float ds = pre > 0.f ? dr.w : 0.f;
-        if (ch == 0) {
+        if (cq == 0) {
           dsig_s[row] = ds;
           *reinterpret_cast<float4*>(tsc + (size_t)DLS_BLOCK * BLK + row * 16) = make_float4(dlog[0], dlog[1], dlog[2], ds);
           if (dl_acc) {  // sum of d logits per (shared) embedding row: appearance gradients are finished from it
@@ -348,51 +389,51 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
           }
         }
       }
-#pragma unroll 1
-      for (int q = 0; q < 2; ++q) {
-        const uint32_t col = ch * 64 + q * 32;
+      {
         uint32_t ph[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float g0 = dlog[0] * vec[V_RGBW + col + 2 * j] + dlog[1] * vec[V_RGBW + 128 + col + 2 * j] + dlog[2] * vec[V_RGBW + 256 + col + 2 * j];
-          float g1 = dlog[0] * vec[V_RGBW + col + 2 * j + 1] + dlog[1] * vec[V_RGBW + 128 + col + 2 * j + 1] + dlog[2] * vec[V_RGBW + 256 + col + 2 * j + 1];
-          if (!((hmask[q] >> (2 * j)) & 1u)) g0 = 0.f;
-          if (!((hmask[q] >> (2 * j + 1)) & 1u)) g1 = 0.f;
-          ph[j] = pack_bf16x2(g0, g1);
+          const uint32_t c0 = dcol + 2 * j;
+          const float g0 = dlog[0] * vec[V_RGBW + c0] + dlog[1] * vec[V_RGBW + 128 + c0] + dlog[2] * vec[V_RGBW + 256 + c0];
+          const float g1 = dlog[0] * vec[V_RGBW + c0 + 1] + dlog[1] * vec[V_RGBW + 128 + c0 + 1] + dlog[2] * vec[V_RGBW + 256 + c0 + 1];
+          ph[j] = gate_pack(g0, g1, hmask, j);
         }
-        tmem_st16(tlane + COL_AHI + (col >> 1), ph);
-        store_row32(tsc, ZB_DIR, row, col, ph);
+        tmem_st16(tlane + COL_AHI + (dcol >> 1), ph);
+        store_row32(tsc, ZB_DIR, row, dcol, ph);
       }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(a_ready);
-      named_bar_sync(1, EPI_THREADS);  // dsig_s visible to the ch == 1 warps
+      named_bar_sync(1, P1_EPI_THREADS);  // dsig_s visible to every column quarter
 
-      // ---- dgrad epilogues, layer 7 down to 0: dZ_l = dH_{l+1} * [H_{l+1} > 0] ----
+      // ---- dgrad epilogues, layer 7 down to 0: dZ_l = dH_{l+1} * gate_l ----
       for (int l = NERFW_LAYERS - 1; l >= 0; --l) {
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        const uint32_t* mw = mask_words(sm, l, row, ch);
         const float ds = dsig_s[row];
+        const uint64_t ds2 = pack2f(ds, ds);
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t col = ch * 128 + q * 32;
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t col = cq * 64 + q * 32;
           uint32_t r[32];
           tmem_ld32(tlane + COL_ACC + col, r);
           tmem_wait_ld();
-          const uint32_t bits = fwd_masks ? __ldg(fwd_masks + mask_index(tile, l, row, ch, q)) : mw[q];
+          const uint32_t bits = fwd_masks ? __ldg(fwd_masks + mask_index(tile, l, row, 0, (int)(col >> 5)))
+                                          : mask_words(sm, l, row)[col >> 5];
           uint32_t ph[16];
+          if (l == NERFW_LAYERS - 1) {  // + density head: d sigma_pre * w_sigma
+            const float2* w2 = reinterpret_cast<const float2*>(vec + V_DENW + col);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float g0 = __uint_as_float(r[2 * j]), g1 = __uint_as_float(r[2 * j + 1]);
-            if (l == NERFW_LAYERS - 1) {  // + density head: d sigma_pre * w_sigma
-              g0 = fmaf(ds, vec[V_DENW + col + 2 * j], g0);
-              g1 = fmaf(ds, vec[V_DENW + col + 2 * j + 1], g1);
+            for (int j = 0; j < 16; ++j) {
+              const float2 ww = w2[j];
+              float g0, g1;
+              unpack2f(fma2(ds2, pack2f(ww.x, ww.y), pack2(r[2 * j], r[2 * j + 1])), g0, g1);
+              ph[j] = gate_pack(g0, g1, bits, j);
             }
-            if (!((bits >> (2 * j)) & 1u)) g0 = 0.f;
-            if (!((bits >> (2 * j + 1)) & 1u)) g1 = 0.f;
-            ph[j] = pack_bf16x2(g0, g1);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ph[j] = gate_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), bits, j);
           }
           if (l > 0) tmem_st16(tlane + COL_AHI + (col >> 1), ph);
           store_row32(tsc, ZB(l), row, col, ph);
@@ -409,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == P1_MMA_WARP) {
     __syncwarp();
     tmem_dealloc<512>(tmem);
   }
@@ -854,7 +895,7 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   }
   const int sms = sm_count();
   int64_t grid1 = ntiles < sms ? ntiles : sms;
-  tcb::mlp_tc_bwd_pass1_kernel<<<(unsigned)grid1, tc::THREADS, tcb::SMEM1_BYTES, st>>>(
+  tcb::mlp_tc_bwd_pass1_kernel<<<(unsigned)grid1, tcb::P1_THREADS, tcb::SMEM1_BYTES, st>>>(
       reinterpret_cast<const uint8_t*>(packed), src, emb ? reinterpret_cast<const float4*>(app_off) : nullptr,
       emb ? app_vec : nullptr, reinterpret_cast<const float4*>(d_raw), total, scratch, emb ? dl_acc : nullptr,
       reinterpret_cast<const uint32_t*>(relu_masks));

@@ -63,10 +63,7 @@ def test_trainer_step_matches_torch_loop(state_dict, oracle):
     opt = torch.optim.Adam(list(models[1].parameters()) + [tables[1]], lr=5e-4)
     losses = []
     for step in range(2):
-        torch.manual_seed(100 + step)
-        t_rand = torch.rand(96, 64, device="cuda")
-        # same uniforms for both paths
-        torch.manual_seed(100 + step)
+        torch.manual_seed(100 + step)   # same device RNG state -> same stratified jitter for both paths
         la = tr.step(o, d, tgt, 2, 2.0, 6.0, 64, 0, perturb=True)
         torch.manual_seed(100 + step)
         opt.zero_grad()
@@ -77,12 +74,18 @@ def test_trainer_step_matches_torch_loop(state_dict, oracle):
         opt.step()
         losses.append((float(la), float(lb)))
         assert abs(float(la) - float(lb)) <= 1e-6
-    worst = 0.0
+    # gradients of the last step agree to fp32 summation-order noise (both backward passes accumulate with atomics)
     for (k, pa), (_, pb) in zip(models[0].named_parameters(), models[1].named_parameters()):
-        worst = max(worst, maxabs(pa, pb))
-    worst = max(worst, maxabs(tables[0], tables[1]))
-    record("trainer_vs_torch_loop", worst_param_abs=worst)
-    assert worst <= 1e-5, worst   # atomics make the gradient summation order vary run to run
+        rel = maxabs(pa.grad, pb.grad) / (float(pb.grad.abs().max()) + 1e-20)
+        assert rel <= 1e-4, (k, rel)
+    # parameters: Adam normalises every element to a step of ~lr, so an element whose tiny gradient changes sign with the
+    # summation order may move the other way: bound the worst case by 2 steps x 2 lr and require 99.9 % within 2e-6
+    diffs = torch.cat([(pa - pb).abs().reshape(-1) for (_, pa), (_, pb) in
+                       zip(models[0].named_parameters(), models[1].named_parameters())] + [(tables[0] - tables[1]).abs().reshape(-1)])
+    worst = float(diffs.max())
+    frac_close = float((diffs <= 2e-6).float().mean())
+    record("trainer_vs_torch_loop", worst_param_abs=worst, frac_within_2e6=frac_close)
+    assert worst <= 4 * 5e-4 and frac_close >= 0.999, (worst, frac_close)
     assert float(tables[0][0].sub(tables[1][0]).abs().max()) == 0.0   # untouched rows stay equal
 
 
