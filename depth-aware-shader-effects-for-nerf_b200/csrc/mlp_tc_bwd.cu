@@ -110,6 +110,30 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int block0, uint32_t 
   }
 }
 
+// Same data through a per-warp 2 KB shared-memory staging buffer, so that four consecutive lanes write the 64 contiguous
+// bytes of one row: a warp store then touches 8 cache lines instead of 32 (scattered 16-byte stores cost one LSU cycle per
+// line and were the bottleneck of this kernel).  Slot rotation by row/2 keeps both the staging writes and reads at the
+// 4-wavefront minimum.  `stage` is this warp's buffer; only used when the mask region of shared memory is free.
+__device__ __forceinline__ void store_row32_staged(uint8_t* stage, uint8_t* tile, int block0, uint32_t row0, uint32_t lane,
+                                                   uint32_t col, const uint32_t (&p)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t slot = (c + (lane >> 1)) & 3;
+    *reinterpret_cast<uint4*>(stage + lane * 64 + slot * 16) = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+  }
+  __syncwarp();
+  uint8_t* blk = tile + (size_t)(block0 + (col >> 6)) * BLK;
+  const uint32_t k0 = col & 63;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t r = 8 * i + (lane >> 2), c = lane & 3;
+    const uint32_t slot = (c + (r >> 1)) & 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 64 + slot * 16);
+    *reinterpret_cast<uint4*>(blk + sw128_offset(row0 + r, k0 + 8 * c)) = v;
+  }
+  __syncwarp();
+}
+
 // ====================================================================================================================
 __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint8_t* __restrict__ packed, SampleSource src,
                                                                        const float4* __restrict__ app_off,
@@ -233,6 +257,12 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
     uint32_t acc_phase = 0;
     uint8_t* pex = sm + SM_PEX_HI;
     uint8_t* ped = sm + SM_PED_HI;
+    // with the forward's gates the mask region of shared memory is free: 16 x 2 KB staging buffers for coalesced stores
+    uint8_t* stage = fwd_masks ? sm + (warp < 8 ? SM1_MASK_A : SM1_MASK_B) + (warp & 7) * 2048 : nullptr;
+    auto put = [&](uint8_t* tile_base, int block0, uint32_t col, const uint32_t (&p)[16]) {
+      if (stage) store_row32_staged(stage, tile_base, block0, quad * 32, lane, col, p);
+      else store_row32(tile_base, block0, row, col, p);
+    };
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t s = tile * TM + row;
       const bool live = s < n_total;
@@ -319,7 +349,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
             for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           }
           tmem_st16(tlane + COL_AHI + (col >> 1), ph);
-          store_row32(tsc, XB_H(layer + 1), row, col, ph);
+          put(tsc, XB_H(layer + 1), col, ph);
         }
         tmem_wait_st();
         tc_fence_before();
@@ -350,7 +380,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(hv[2 * j] + appv[dcol + 2 * j], hv[2 * j + 1] + appv[dcol + 2 * j + 1]);
-        store_row32(tsc, XB_HDT, row, dcol, ph);
+        put(tsc, XB_HDT, dcol, ph);
         hmask = fwd_masks ? __ldg(fwd_masks + mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))) : bits;
       }
       tc_fence_before();
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
           ph[j] = gate_pack(g0, g1, hmask, j);
         }
         tmem_st16(tlane + COL_AHI + (dcol >> 1), ph);
-        store_row32(tsc, ZB_DIR, row, dcol, ph);
+        put(tsc, ZB_DIR, dcol, ph);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -408,19 +438,23 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
 
       // ---- dgrad epilogues, layer 7 down to 0: dZ_l = dH_{l+1} * gate_l ----
       for (int l = NERFW_LAYERS - 1; l >= 0; --l) {
+        // gate words for this layer, fetched before the accumulator wait so their latency is hidden behind the MMAs
+        uint32_t gate[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          gate[q] = fwd_masks ? __ldg(fwd_masks + mask_index(tile, l, row, 0, (int)(cq * 2 + q))) : 0u;
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
         const float ds = dsig_s[row];
         const uint64_t ds2 = pack2f(ds, ds);
-#pragma unroll 1
+#pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint32_t col = cq * 64 + q * 32;
           uint32_t r[32];
           tmem_ld32(tlane + COL_ACC + col, r);
           tmem_wait_ld();
-          const uint32_t bits = fwd_masks ? __ldg(fwd_masks + mask_index(tile, l, row, 0, (int)(col >> 5)))
-                                          : mask_words(sm, l, row)[col >> 5];
+          const uint32_t bits = fwd_masks ? gate[q] : mask_words(sm, l, row)[col >> 5];
           uint32_t ph[16];
           if (l == NERFW_LAYERS - 1) {  // + density head: d sigma_pre * w_sigma
             const float2* w2 = reinterpret_cast<const float2*>(vec + V_DENW + col);
@@ -436,7 +470,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
             for (int j = 0; j < 16; ++j) ph[j] = gate_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), bits, j);
           }
           if (l > 0) tmem_st16(tlane + COL_AHI + (col >> 1), ph);
-          store_row32(tsc, ZB(l), row, col, ph);
+          put(tsc, ZB(l), col, ph);
         }
         if (l > 0) {
           tmem_wait_st();

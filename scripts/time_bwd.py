@@ -18,12 +18,13 @@ params = {k: t.detach() for k, t in zip(names, tensors)}
 packed = m.packed_weights(names, tensors)
 g = {k: torch.zeros_like(t) for k, t in params.items()}
 de = torch.zeros(1, 32, device="cuda")
+_, masks = ops.mlp_fwd(params, packed, o, d, z, e, 1, want_masks=True)
 for _ in range(2):
-    ops.mlp_bwd_tc(params, g, packed, o, d, z, e, d_raw, de)
+    ops.mlp_bwd_tc(params, g, packed, o, d, z, e, d_raw, de, masks)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(5):
-    ops.mlp_bwd_tc(params, g, packed, o, d, z, e, d_raw, de)
+    ops.mlp_bwd_tc(params, g, packed, o, d, z, e, d_raw, de, masks)
 e1.record(); torch.cuda.synchronize()
 print("NERFW_WGRAD_DEBUG=%s  bwd_tc total %.3f ms per call (pass1 + wgrad), %d tiles" % (os.environ.get("NERFW_WGRAD_DEBUG", "0"), e0.elapsed_time(e1) / 5, b * n // 128))
