@@ -356,8 +356,20 @@ def run_ours(args):
         torch.cuda.synchronize()
         rms = comp0.elapsed_time(comp1) / 5
         rbytes = n_rays * (3 * N_COARSE + 2 * N_IMPORTANCE) * 4.0
+        g_rgb = torch.rand((n_rays, 3), device=dev)
+        g_depth = torch.rand((n_rays, 1), device=dev)
+        ops.composite_bwd(raw, z_fine, g_rgb, g_depth, None, None)
+        comp0.record()
+        for _ in range(5):
+            ops.composite_bwd(raw, z_fine, g_rgb, g_depth, None, None)
+        comp1.record()
+        torch.cuda.synchronize()
+        bms = comp0.elapsed_time(comp1) / 5
+        bbytes = z_fine.numel() * 40.0
         hbm = {"composite_fwd": {"bound": "hbm", "achieved": cbytes / (cms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                  "unit": "GB/s", "frac": cbytes / (cms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": cms},
+               "composite_bwd": {"bound": "hbm", "achieved": bbytes / (bms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                 "unit": "GB/s", "frac": bbytes / (bms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": bms},
                "sample_pdf": {"bound": "hbm", "achieved": rbytes / (rms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                               "unit": "GB/s", "frac": rbytes / (rms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": rms}}
 

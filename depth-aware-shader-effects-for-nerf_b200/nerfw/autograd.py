@@ -23,6 +23,27 @@ def backward_uses_tensor_cores(mode: int, emb) -> bool:
     return mode != MLP_FP32 and (emb is None or emb.shape[0] == 1)
 
 
+# Optional gradient sink: {parameter name: tensor}.  While set (nerfw.train.Trainer does, with views into its flat gradient
+# buffer), the backward kernels accumulate straight into these tensors and autograd receives None for the parameters,
+# which removes ~100 zero-fill / add launches per training step.  Plain `loss.backward()` users never see it.
+_GRAD_SINK = None
+
+
+class grad_sink:
+    def __init__(self, sink: dict):
+        self.sink = sink
+
+    def __enter__(self):
+        global _GRAD_SINK
+        self.prev, _GRAD_SINK = _GRAD_SINK, self.sink
+        return self
+
+    def __exit__(self, *exc):
+        global _GRAD_SINK
+        _GRAD_SINK = self.prev
+        return False
+
+
 def _param_dict(names, tensors):
     return {n: t for n, t in zip(names, tensors)}
 
@@ -41,12 +62,16 @@ def _mlp_backward(ctx, d_raw):
         emb = saved[k]
         k += 1
     params = _param_dict(names, saved[k:k + len(names)])
-    grads = {n: torch.zeros_like(t) for n, t in params.items()}
+    sink = _GRAD_SINK
+    direct = sink is not None and all(n in sink for n in params)
+    grads = {n: sink[n] for n in params} if direct else {n: torch.zeros_like(t) for n, t in params.items()}
     d_emb = torch.zeros_like(emb) if emb is not None else None
     if ctx.packed is not None and backward_uses_tensor_cores(ctx.mode, emb):
         ops.mlp_bwd_tc(params, grads, ctx.packed, p, d, z, emb, d_raw.contiguous(), d_emb, ctx.masks)
     else:
         ops.mlp_bwd(params, grads, p, d, z, emb, d_raw.contiguous(), d_emb)
+    if direct:
+        grads = {n: None for n in params}   # already accumulated in place
     return grads, d_emb
 
 

@@ -14,6 +14,7 @@ from typing import Optional
 import torch
 
 from . import ops
+from .autograd import grad_sink
 from .parallel import FlatParams, shard_bounds, world_info
 from .render import volume_render
 
@@ -65,7 +66,9 @@ class Trainer:
             outs.append(extras["rgb_coarse"])
             grads.append(d_c)
             loss = loss + loss_c
-        torch.autograd.backward(outs, grads)
+        # the MLP backward kernels accumulate straight into the flat gradient buffer (views keyed by parameter name)
+        with grad_sink({n: p.grad for n, p in self.model.named_parameters()}):
+            torch.autograd.backward(outs, grads)
         self.flat.all_reduce(self.group)
         self.step_count += 1
         ops.adam_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,

@@ -1,15 +1,33 @@
 #!/bin/bash
-# ncu evidence for one whole-frame render: (1) every launch with its device time, (2) full-set capture of the MLP kernel
-# and the HBM-bound kernels.  Plain run first; ncu only if it exits 0.
+# ncu evidence for profiles/: (1) launch list of bench.py itself, (2) --set full captures of every hot-path kernel on
+# small fixed workloads (one 200-row crop of the frame per MLP mode, one training step).  Plain run first, ncu only if it
+# exits 0 (B200_PROFILING.md).  Reports are exported to CSV on the box and deleted (gpurun_out/ may carry 64 MiB back).
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
-MODE=${1:-bf16x3}
-python scripts/profile_frame.py --mode $MODE > gpurun_out/profile_plain_$MODE.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$MODE.csv \
-    python scripts/profile_frame.py --mode $MODE > gpurun_out/ncu_launches_$MODE.log 2>&1
-echo "launch list rc=$?"
-python scripts/profile_frame.py --mode $MODE --rows 200 > gpurun_out/profile_plain200_$MODE.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'mlp_tc_fwd|composite_fwd|sample_pdf|stratified|raygen' \
-    -o gpurun_out/prof_$MODE -f python scripts/profile_frame.py --mode $MODE --rows 200 > gpurun_out/ncu_full_$MODE.log 2>&1
-echo "full capture rc=$?"
-ls -la gpurun_out | tail -20
+export_rep () {  # $1 = report stem, $2.. = kernel regexes for source pages
+  local stem=$1; shift
+  ncu -i gpurun_out/$stem.ncu-rep --page raw --csv > gpurun_out/${stem}_raw.csv 2>/dev/null
+  for k in "$@"; do
+    ncu -i gpurun_out/$stem.ncu-rep --page source --csv --kernel-name regex:$k > gpurun_out/${stem}_src_$k.csv 2>/dev/null
+  done
+  rm -f gpurun_out/$stem.ncu-rep
+}
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+$BENCH > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv $BENCH > gpurun_out/ncu_bench.log 2>&1
+echo "bench launch list rc=$?"
+for MODE in bf16x3 bf16; do
+  python scripts/profile_frame.py --mode $MODE --rows 200 > gpurun_out/pf_$MODE.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:'mlp_tc_fwd|composite_fwd|sample_pdf|stratified|raygen|normalize' \
+      -o gpurun_out/prof_frame_$MODE -f python scripts/profile_frame.py --mode $MODE --rows 200 > gpurun_out/ncu_frame_$MODE.log 2>&1
+  echo "frame $MODE rc=$?"
+  export_rep prof_frame_$MODE mlp_tc_fwd
+done
+python scripts/profile_train.py bf16x3 1 > gpurun_out/pt.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'pass1|wgrad|composite_bwd|adam|mse|app_' \
+    -o gpurun_out/prof_train -f python scripts/profile_train.py bf16x3 1 > gpurun_out/ncu_train_full.log 2>&1
+echo "train rc=$?"
+export_rep prof_train pass1 wgrad
+python scripts/profile_train.py bf16x3 2 > gpurun_out/pt2.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train.csv python scripts/profile_train.py bf16x3 2 > gpurun_out/ncu_train_l.log 2>&1
+du -sh gpurun_out; ls -la gpurun_out | head -40
