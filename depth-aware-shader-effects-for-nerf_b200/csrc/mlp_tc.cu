@@ -78,23 +78,33 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(NerfwWeights w, uint8
 }
 
 // appearance: off[row] = W_rgb (W_app e_row + b_app)  (src/models.py:146-160; the projection is added after the ReLU of
-// the direction layer, so its effect on the rgb logits is this per-embedding 3-vector).  One warp per row.
+// the direction layer, so its effect on the rgb logits is this per-embedding 3-vector).  One 128-thread CTA per row:
+// thread k forms a_k (32 MACs), then three warps reduce a against the three rows of W_rgb.
 __global__ void __launch_bounds__(128) app_offset_kernel(NerfwWeights w, const float* __restrict__ emb, int64_t rows,
                                                          float4* __restrict__ out) {
-  int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float e = __ldg(emb + row * NERFW_APP_DIM + lane);  // APP_DIM == 32 == warp size
-  float o3[3] = {0.f, 0.f, 0.f};
-  for (int k = 0; k < NERFW_DIR_HIDDEN; ++k) {
-    float p = __ldg(w.app_w + k * NERFW_APP_DIM + lane) * e;
+  __shared__ float a_s[NERFW_DIR_HIDDEN];
+  __shared__ float e_s[NERFW_APP_DIM];
+  __shared__ float o_s[3];
+  const int k = threadIdx.x, lane = k & 31, warp = k >> 5;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    if (k < NERFW_APP_DIM) e_s[k] = __ldg(emb + row * NERFW_APP_DIM + k);
+    __syncthreads();
+    float a = __ldg(w.app_b + k);
+#pragma unroll 8
+    for (int q = 0; q < NERFW_APP_DIM; ++q) a = fmaf(__ldg(w.app_w + k * NERFW_APP_DIM + q), e_s[q], a);
+    a_s[k] = a;
+    __syncthreads();
+    if (warp < 3) {
+      float p = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    float a = p + __ldg(w.app_b + k);
+      for (int j = 0; j < 4; ++j) p = fmaf(__ldg(w.rgb_w + warp * NERFW_DIR_HIDDEN + lane + 32 * j), a_s[lane + 32 * j], p);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) o3[c] = fmaf(__ldg(w.rgb_w + c * NERFW_DIR_HIDDEN + k), a, o3[c]);
+      for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if (lane == 0) o_s[warp] = p;
+    }
+    __syncthreads();
+    if (k == 0) out[row] = make_float4(o_s[0], o_s[1], o_s[2], 0.f);
   }
-  if (lane == 0) out[row] = make_float4(o3[0], o3[1], o3[2], 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -462,7 +472,7 @@ int launch_pack_weights(const NerfwWeights& w, void* packed, cudaStream_t stream
 }
 
 int launch_app_offset(const NerfwWeights& w, const float* emb, int64_t emb_rows, float* app_off, cudaStream_t stream) {
-  tc::app_offset_kernel<<<(unsigned)ceil_div64(emb_rows, 4), 128, 0, stream>>>(w, emb, emb_rows, reinterpret_cast<float4*>(app_off));
+  tc::app_offset_kernel<<<(unsigned)(emb_rows < 4096 ? emb_rows : 4096), 128, 0, stream>>>(w, emb, emb_rows, reinterpret_cast<float4*>(app_off));
   NERFW_LAUNCHED();
   return NERFW_OK;
 }
