@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
   const int64_t ntiles = (n_total + TM - 1) / TM;
+  // Split (3-MMA) arithmetic for the direction layer only in training mode: its ReLU gates then match the fp32 forward.
+  // For inference the layer runs as a single bf16 MMA -- it only feeds the rgb sigmoid (sigma, hence depth, acc and the
+  // resampling, come from the trunk); measured effect on rendered rgb <= 5e-5.
+  const bool dir_split = X3 && masks != nullptr;
 
   if (warp == F_PRODUCER_WARP) {
     // ===================== weight producer =====================
@@ -157,8 +161,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         size_t off = 0;
         for (int i = 0; i < N_CHUNKS; ++i) {
           const uint32_t sz = i < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
-#pragma unroll
-          for (int v = 0; v < (X3 ? 2 : 1); ++v) {
+          const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
+          for (int v = 0; v < copies; ++v) {
             mbar_wait(&empty[p.stage], p.phase ^ 1);
             mbar_arrive_expect_tx(&full[p.stage], sz);
             bulk_g2s(sm + SM_RING + p.stage * BIG_CHUNK, packed + off + (size_t)v * sz, sz, &full[p.stage]);
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       const uint32_t ring = smem_u32(sm + SM_RING);
       const uint32_t d_acc = tmem + COL_ACC;
       // one 64-wide K block: A (hi[,lo]) x W chunk (hi[,lo]); a_* are either TMEM addresses (TS) or smem descs (SS)
-      auto kblock = [&](bool from_tmem, uint64_t a_hi, uint64_t a_lo, uint32_t idesc, int ksteps, bool first) {
+      auto kblock = [&](bool from_tmem, uint64_t a_hi, uint64_t a_lo, uint32_t idesc, int ksteps, bool first, bool split = X3) {
         mbar_wait(&full[p.stage], p.phase);
         tc_fence_after();
         uint64_t b = smem_desc_sw128(ring + p.stage * BIG_CHUNK);
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           if (from_tmem) mma_ts(d_acc, (uint32_t)a_hi + 8 * k, b + 2 * k, idesc, accf);
           else mma_ss(d_acc, a_hi + 2 * k, b + 2 * k, idesc, accf);
         }
-        if (X3) {
+        if (split) {
           for (int k = 0; k < ksteps; ++k) {
             if (from_tmem) mma_ts(d_acc, (uint32_t)a_lo + 8 * k, b + 2 * k, idesc, 1u);
             else mma_ss(d_acc, a_lo + 2 * k, b + 2 * k, idesc, 1u);
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         }
         mma_commit(&empty[p.stage]);
         p.advance();
-        if (X3) {
+        if (split) {
           mbar_wait(&full[p.stage], p.phase);
           tc_fence_after();
           uint64_t bl = smem_desc_sw128(ring + p.stage * BIG_CHUNK);
@@ -225,8 +229,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           mma_commit(acc_full);
         }
         wait_a();
-        for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, kb == 0);
-        kblock(false, ped_hi, ped_lo, idesc128, 2, false);
+        for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, kb == 0, dir_split);
+        kblock(false, ped_hi, ped_lo, idesc128, 2, false, dir_split);
         mma_commit(acc_full);
       }
     }
@@ -239,8 +243,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     uint8_t* pex_hi = sm + SM_PEX_HI;
     uint8_t* pex_lo = sm + SM_PEX_LO;
     uint8_t* ped_hi = sm + SM_PED_HI;
-    uint8_t* ped_lo = sm + SM_PED_LO;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t s = tile * TM + row;
       const bool live = s < n_total;
       // ---- encodings: quarter 0 / 1 -> position features 0..31 / 32..63, quarter 2 -> the direction tile ----
@@ -258,7 +261,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           float d[3] = {0.f, 0.f, 0.f};
           if (live) src.direction(s, d);
           dir_features32<!X3>(d, v);
-          store_features32<X3>(ped_hi, ped_lo, row, 0, v);
+          if (dir_split) store_features32<true>(ped_hi, sm + SM_PED_LO, row, 0, v);
+          else store_features32<false>(ped_hi, ped_hi, row, 0, v);
         }
       }
       fence_proxy_async_smem();
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
 #pragma unroll
             for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             tmem_st16(tlane + COL_AHI + (col >> 1), ph);
-            if (X3) {
+            if (X3 && (layer != NERFW_LAYERS - 1 || dir_split)) {  // inference: the direction layer consumes A_hi only
               uint32_t pl[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {

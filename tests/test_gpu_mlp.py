@@ -7,8 +7,9 @@ from gpu_util import maxabs, record
 
 pytestmark = pytest.mark.gpu
 
-# max-abs bounds on (rgb, sigma) of one MLP evaluation at random init (|sigma| ~ 0.1, rgb ~ 0.5)
-FWD_TOL = {"fp32": (2e-6, 2e-6), "bf16x3": (2e-5, 2e-5), "bf16": (8e-3, 8e-3)}
+# max-abs bounds on (rgb, sigma) of one MLP evaluation at random init (|sigma| ~ 0.1, rgb ~ 0.5).  In bf16x3 inference the
+# direction layer (which only feeds the rgb sigmoid) runs as a single bf16 MMA: per-sample rgb 7e-5, sigma stays 1e-7.
+FWD_TOL = {"fp32": (2e-6, 2e-6), "bf16x3": (5e-4, 2e-5), "bf16": (8e-3, 8e-3)}
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -100,7 +101,7 @@ def test_mlp_ray_form_equals_sample_form(cuda_model):
         assert torch.equal(a, b_), mode   # identical arithmetic, only the addressing differs
 
 
-@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("bf16", 1.5e-2)])
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 5e-4), ("bf16", 1.5e-2)])
 def test_tensor_core_mlp_vs_fp32_kernel_large(cuda_model, mode, tol):
     """200k samples (1563 tiles over 148 persistent CTAs): exercises the weight ring, phase wrap-around and tile loop."""
     model, emb = cuda_model
@@ -115,8 +116,11 @@ def test_tensor_core_mlp_vs_fp32_kernel_large(cuda_model, mode, tol):
         got = model.run_mlp(o, d, z, e, mode)
         again = model.run_mlp(o, d, z, e, mode)
     err = maxabs(got, ref)
-    record(f"mlp_tc_vs_ffma_{mode}", maxabs=err)
+    err_sigma = maxabs(got[:, 3], ref[:, 3])
+    record(f"mlp_tc_vs_ffma_{mode}", maxabs=err, sigma=err_sigma)
     assert err <= tol, err
+    if mode == "bf16x3":
+        assert err_sigma <= 3e-5, err_sigma   # the trunk (density) keeps the 3-term split
     assert torch.equal(got, again)   # deterministic
 
 
@@ -236,3 +240,19 @@ def test_tensor_core_backward_without_forward_gates(cuda_model):
         ref, got = g_ref[k].double(), g_tc[k].double()
         cos = float((ref * got).sum() / (ref.norm() * got.norm() + 1e-30))
         assert cos >= 0.99, (k, cos)
+
+
+def test_training_forward_keeps_split_direction_layer(cuda_model, golden):
+    """With ReLU masks requested (training) the bf16x3 forward also splits the direction layer: fp32-level rgb."""
+    from nerfw import ops
+    model, emb = cuda_model
+    g = golden("mlp_64")
+    x, d = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["d"]).cuda()
+    names, tensors = model.kernel_params()
+    params = {k: t.detach() for k, t in zip(names, tensors)}
+    packed = model.packed_weights(names, tensors)
+    raw, masks = ops.mlp_fwd(params, packed, x, d, None, emb.unsqueeze(0).contiguous(), 1, want_masks=True)
+    e_rgb, e_sig = maxabs(raw[:, :3], g["rgb"]), maxabs(raw[:, 3:], g["sigma"])
+    record("mlp_fwd_golden_bf16x3_training", rgb=e_rgb, sigma=e_sig)
+    assert e_rgb <= 2e-5 and e_sig <= 2e-5, (e_rgb, e_sig)
+    assert masks.numel() == 9 * 128 * 8 * 4
