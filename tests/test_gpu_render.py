@@ -247,3 +247,31 @@ def test_high_sample_stress_config(cuda_model, oracle, state_dict, mode):
     record(f"stress_256_512_{mode}", **e)
     t = TOL[mode]
     assert e["rgb"] <= t[0] and e["depth"] <= t[1] and e["acc"] <= t[2], e
+
+
+def test_full_frame_properties(cuda_model):
+    """BASELINE.json configs[1] at full size (800x800, 64+128) through the whole-frame call: value ranges that hold for any
+    weights, determinism, and independence of where a ray sits in the batch (tile / CTA assignment)."""
+    import nerfw
+    from nerfw.camera import aligned_spiral_poses, blender_focal
+    from nerfw.frame import render_frame
+    model, emb = cuda_model
+    pose = aligned_spiral_poses(120, 2, "x", "chair")[0]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rgb, depth, acc = render_frame(model, 800, 800, blender_focal(800), pose, 2.0, 6.0, 64, 128, appearance_embedding=emb, generator=g)
+    assert rgb.shape == (800, 800, 3) and depth.shape == (800, 800) and acc.shape == (800, 800)
+    assert bool(torch.isfinite(rgb).all()) and bool(torch.isfinite(depth).all())
+    assert float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0 + 1e-5        # sum w * sigmoid with sum w <= 1
+    assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-5
+    hit = acc > 1e-6
+    assert float(depth[hit].min()) >= 2.0 - 1e-3 and float(depth[hit].max()) <= 6.0 + 1e-3
+    g2 = torch.Generator(device="cuda").manual_seed(11)
+    rgb2, depth2, _ = render_frame(model, 800, 800, blender_focal(800), pose, 2.0, 6.0, 64, 128, appearance_embedding=emb, generator=g2)
+    assert torch.equal(rgb, rgb2) and torch.equal(depth, depth2)
+    # coarse pass (no randomness): a 4096-ray slice rendered alone equals the same rays inside the whole frame
+    o, d = nerfw.get_rays(800, 800, blender_focal(800), torch.from_numpy(pose).cuda())
+    o, d = o.reshape(-1, 3).contiguous(), d.reshape(-1, 3)
+    with torch.no_grad():
+        whole = nerfw.volume_render(model, o, d, 2.0, 6.0, 64, 0, appearance_embedding=emb, perturb=False)
+        part = nerfw.volume_render(model, o[333333:337429], d[333333:337429], 2.0, 6.0, 64, 0, appearance_embedding=emb, perturb=False)
+    assert torch.equal(whole[0][333333:337429], part[0]) and torch.equal(whole[1][333333:337429], part[1])
