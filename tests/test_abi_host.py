@@ -119,3 +119,25 @@ def test_mode_names():
     assert resolve_mode("fp32") == 0 and resolve_mode("bf16x3") == 1 and resolve_mode("BF16") == 2
     with pytest.raises(ValueError):
         resolve_mode("fp8")
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without libnerfw_sm100.so the loader raises ImportError naming the build command."""
+    from nerfw import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libnerfw_sm100.so"))
+    with pytest.raises(ImportError, match="not built|not found"):
+        _lib.lib()
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package may reference it."""
+    pkg = os.path.join(ROOT, "depth-aware-shader-effects-for-nerf_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"nerfw_oracle|from oracle|import oracle|oracle/", text):
+                    offenders.append(os.path.join(base, f))
+    assert offenders == []
