@@ -275,3 +275,26 @@ def test_full_frame_properties(cuda_model):
         whole = nerfw.volume_render(model, o, d, 2.0, 6.0, 64, 0, appearance_embedding=emb, perturb=False)
         part = nerfw.volume_render(model, o[333333:337429], d[333333:337429], 2.0, 6.0, 64, 0, appearance_embedding=emb, perturb=False)
     assert torch.equal(whole[0][333333:337429], part[0]) and torch.equal(whole[1][333333:337429], part[1])
+
+
+@pytest.mark.parametrize("n,ni", [(37, 53), (8, 200), (2, 1), (130, 64)])
+def test_odd_sample_counts_end_to_end(cuda_model, oracle, state_dict, n, ni):
+    """Sample counts that are multiples of nothing (tile / warp / chunk remainders everywhere) vs the composed oracle."""
+    import nerfw
+    model, emb = cuda_model
+    sd, emb_cpu = state_dict
+    o, d = view(oracle)
+    sel = torch.arange(3, 10000, 131, device="cuda")[:70]
+    oc, dc = o.reshape(-1, 3)[sel].contiguous(), d.reshape(-1, 3)[sel].contiguous()
+    torch.manual_seed(n * 1000 + ni)
+    u = torch.rand(70, ni)
+    t = torch.rand(70, n)
+    with torch.no_grad():
+        rgb_o, depth_o, ex_o = oracle.render_hier(sd, sd, oc.cpu(), dc.cpu(), 2.0, 6.0, n, ni, emb=emb_cpu, perturb=True,
+                                                  t_rand=t, u_rand=u)
+        rgb, depth, ex = nerfw.volume_render(model, oc, dc, 2.0, 6.0, n, ni, appearance_embedding=emb, perturb=True,
+                                             mlp_dtype="bf16x3", t_rand=t, u_rand=u)
+    assert ex["z_vals"].shape == (70, n + ni) and torch.equal(ex["z_vals_coarse"].cpu(), ex_o["z_vals_coarse"])
+    e = dict(rgb=maxabs(rgb, rgb_o), depth=maxabs(depth, depth_o), acc=maxabs(ex["acc"], ex_o["acc"]))
+    record(f"odd_counts_{n}_{ni}", **e)
+    assert e["rgb"] <= 1e-3 and e["depth"] <= 2e-3 and e["acc"] <= 1e-3, e
