@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   if (warp == F_PRODUCER_WARP && lane == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(a_ready, F_EPI_THREADS);
+    mbar_init(a_ready, F_EPI_WARPS);   // one arrival per epilogue warp
     fence_mbar_init();
   }
   if (warp == F_MMA_WARP) tmem_alloc<512>(tmem_ptr);
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(a_ready);
+      mbar_arrive_warp(a_ready);
 
       // ---- trunk epilogues: acc -> bias, ReLU -> bf16 (hi[,lo]) -> next layer's A operand in TMEM ----
       float sig = 0.f;
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(a_ready);
+        mbar_arrive_warp(a_ready);
       }
       sig_part[cq * TM + row] = sig;
 

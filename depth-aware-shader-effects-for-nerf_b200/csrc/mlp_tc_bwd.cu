@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
   if (warp == P1_PRODUCER_WARP && lane == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(a_ready, P1_EPI_THREADS);
+    mbar_init(a_ready, P1_EPI_WARPS);   // one arrival per epilogue warp
     fence_mbar_init();
   }
   if (warp == P1_MMA_WARP) tmem_alloc<512>(tmem_ptr);
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(a_ready);
+      mbar_arrive_warp(a_ready);
       // encodings -> scratch (wgrad operands of layer 0, the skip part of layer 4 and the direction layer)
       named_bar_sync(1, P1_EPI_THREADS);
       {
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(a_ready);
+        mbar_arrive_warp(a_ready);
       }
       sig_part[cq * TM + row] = sig;
 
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(a_ready);
+      mbar_arrive_warp(a_ready);
       named_bar_sync(1, P1_EPI_THREADS);  // dsig_s visible to every column quarter
 
       // ---- dgrad epilogues, layer 7 down to 0: dZ_l = dH_{l+1} * gate_l ----
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         if (l > 0) {
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(a_ready);
+          mbar_arrive_warp(a_ready);
         } else {
           tc_fence_before();
         }
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) mlp_tc_wgrad_kernel(const __gri
   const bool need_dls = (wb.flags & 6) != 0;
 
   if (tid == 0) {
-    for (int i = 0; i < W2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 256); }
+    for (int i = 0; i < W2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 8); }  // MMA commit + one arrival per reducer warp
     mbar_init(done, 1);
     fence_mbar_init();
   }
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) mlp_tc_wgrad_kernel(const __gri
           if (grp == 0) { hb[0] += dl.x; hb[1] += dl.y; hb[2] += dl.z; }
         }
       }
-      mbar_arrive(&empty[stage]);
+      mbar_arrive_warp(&empty[stage]);
       if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
     }
     // ---- flush the CUDA-core partial sums (each of the 8 row sets holds a partial of the same columns) ----
