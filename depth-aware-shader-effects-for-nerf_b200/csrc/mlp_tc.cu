@@ -20,6 +20,7 @@
 #include "mlp_tc.cuh"
 #include "umma.cuh"
 #include "mlp_tc_layout.cuh"
+#include <stdlib.h>
 
 namespace nerfw {
 namespace tc {
@@ -116,10 +117,14 @@ constexpr int F_MMA_WARP = 17;
 constexpr int F_THREADS = 576;
 constexpr int F_EPI_THREADS = F_EPI_WARPS * 32;
 
+// profiling: event stamps (clock64) of CTA 0, third tile: slot -> time.  Only when a timeline buffer is passed.
+#define NERFW_STAMP(slot) do { if (timeline && blockIdx.x == 0 && tile == (int64_t)(2 * gridDim.x)) timeline[slot] = clock64(); } while (0)
+
 template <bool X3>
 __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* __restrict__ packed, SampleSource src,
                                                                  const float4* __restrict__ app_off, int64_t n_total,
-                                                                 float4* __restrict__ raw, uint32_t* __restrict__ masks) {
+                                                                 float4* __restrict__ raw, uint32_t* __restrict__ masks, int debug_skip_weights,
+                                                                 long long* __restrict__ timeline) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -127,6 +132,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   uint64_t* empty = full + NSTAGES;
   uint64_t* acc_full = empty + NSTAGES;
   uint64_t* a_ready = acc_full + 1;
+  // bf16 mode only: per-K-block operand barriers, accumulator-free and encodings-ready barriers (see the epilogue)
+  uint64_t* a_kb = a_ready + 1;
+  uint64_t* acc_free = a_kb + 4;
+  uint64_t* pe_ready = acc_free + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM_TMEMPTR);
   float* vec = reinterpret_cast<float*>(sm + SM_VEC);
   float* sig_part = reinterpret_cast<float*>(sm + SM_SIG);
@@ -136,6 +145,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
     mbar_init(a_ready, F_EPI_WARPS);   // one arrival per epilogue warp
+    for (int i = 0; i < 4; ++i) mbar_init(&a_kb[i], F_EPI_WARPS);
+    mbar_init(acc_free, F_EPI_WARPS);
+    mbar_init(pe_ready, F_EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == F_MMA_WARP) tmem_alloc<512>(tmem_ptr);
@@ -164,8 +176,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
           for (int v = 0; v < copies; ++v) {
             mbar_wait(&empty[p.stage], p.phase ^ 1);
-            mbar_arrive_expect_tx(&full[p.stage], sz);
-            bulk_g2s(sm + SM_RING + p.stage * BIG_CHUNK, packed + off + (size_t)v * sz, sz, &full[p.stage]);
+            if (debug_skip_weights && tile != (int64_t)blockIdx.x) {
+              mbar_arrive(&full[p.stage]);   // profiling only: reuse whatever the stage holds (results are wrong)
+            } else {
+              mbar_arrive_expect_tx(&full[p.stage], sz);
+              bulk_g2s(sm + SM_RING + p.stage * BIG_CHUNK, packed + off + (size_t)v * sz, sz, &full[p.stage]);
+            }
             p.advance();
           }
           off += 2ull * sz;
@@ -217,6 +233,48 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         ar_phase ^= 1;
         tc_fence_after();
       };
+      if constexpr (!X3) {
+        // bf16 mode: the epilogue frees the accumulator as soon as it sits in registers and publishes the next A operand
+        // one 64-wide K block at a time, so the MMAs of layer l+1 start while most of epilogue l is still running.
+        uint32_t ph_free = 0, ph_pe = 0, ph_kb = 0;
+        auto wait_bar = [&](uint64_t* bar, uint32_t phase) {
+          mbar_wait(bar, phase);
+          tc_fence_after();
+        };
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          wait_bar(pe_ready, ph_pe);
+          ph_pe ^= 1;
+          NERFW_STAMP(0);
+          for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
+            wait_bar(acc_free, ph_free);
+            ph_free ^= 1;
+            NERFW_STAMP(10 + layer * 8);       // accumulator free seen by the MMA thread
+            if (layer == 0) {
+              kblock(false, pex_hi, 0, idesc256, 4, true);
+            } else {
+              for (int kb = 0; kb < 4; ++kb) {
+                wait_bar(&a_kb[kb], ph_kb);
+                if (kb == 0) NERFW_STAMP(11 + layer * 8);   // first operand K block seen
+                if (kb == 3) NERFW_STAMP(12 + layer * 8);   // last operand K block seen
+                kblock(true, tmem + COL_AHI + 32 * kb, 0, idesc256, 4, kb == 0);
+              }
+              ph_kb ^= 1;
+              if (layer == NERFW_SKIP) kblock(false, pex_hi, 0, idesc256, 4, false);
+            }
+            mma_commit(acc_full);
+            NERFW_STAMP(13 + layer * 8);       // all MMAs of the layer issued
+          }
+          wait_bar(acc_free, ph_free);
+          ph_free ^= 1;
+          for (int kb = 0; kb < 4; ++kb) {
+            wait_bar(&a_kb[kb], ph_kb);
+            kblock(true, tmem + COL_AHI + 32 * kb, 0, idesc128, 4, kb == 0);
+          }
+          ph_kb ^= 1;
+          kblock(false, ped_hi, 0, idesc128, 2, false);
+          mma_commit(acc_full);
+        }
+      } else {
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
           wait_a();
@@ -233,6 +291,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         kblock(false, ped_hi, ped_lo, idesc128, 2, false, dir_split);
         mma_commit(acc_full);
       }
+      }
     }
   } else {
     // ===================== encoders + epilogues (16 warps, thread <-> sample row x column quarter) ==========
@@ -243,7 +302,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     uint8_t* pex_hi = sm + SM_PEX_HI;
     uint8_t* pex_lo = sm + SM_PEX_LO;
     uint8_t* ped_hi = sm + SM_PED_HI;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if constexpr (!X3) mbar_arrive_warp(acc_free);   // the accumulator starts out free
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t s = tile * TM + row;
       const bool live = s < n_total;
       // ---- encodings: quarter 0 / 1 -> position features 0..31 / 32..63, quarter 2 -> the direction tile ----
@@ -266,10 +326,65 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive_warp(a_ready);
+      if constexpr (X3) mbar_arrive_warp(a_ready); else mbar_arrive_warp(pe_ready);
 
       // ---- trunk epilogues: acc -> bias, ReLU -> bf16 (hi[,lo]) -> next layer's A operand in TMEM ----
       float sig = 0.f;
+      if constexpr (!X3) {
+        // bf16 mode.  Thread <-> (row, 16-column slice cq of every 64-wide K block).  All 64 accumulator values are pulled
+        // into registers first and the accumulator is released; the four slices are then finished and published one K
+        // block at a time, so the next layer's MMAs overlap with three quarters of this epilogue.
+        for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
+          mbar_wait(acc_full, acc_phase);
+          acc_phase ^= 1;
+          tc_fence_after();
+          if (tid == 0) NERFW_STAMP(14 + layer * 8);   // accumulator complete seen by the epilogue
+          const float* bias = vec + V_PTSB + layer * 256;
+          uint32_t r[4][16];
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) tmem_ld16(tlane + COL_ACC + kb * 64 + cq * 16, r[kb]);
+          tmem_wait_ld();
+          tc_fence_before();
+          mbar_arrive_warp(acc_free);
+          if (tid == 0) NERFW_STAMP(15 + layer * 8);   // accumulator in registers
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint32_t col = kb * 64 + cq * 16;
+            const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+            uint32_t ph[8];
+            float a[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bb = b4[j4];
+              unpack2f(add2(pack2(r[kb][4 * j4], r[kb][4 * j4 + 1]), pack2f(bb.x, bb.y)), a[4 * j4], a[4 * j4 + 1]);
+              unpack2f(add2(pack2(r[kb][4 * j4 + 2], r[kb][4 * j4 + 3]), pack2f(bb.z, bb.w)), a[4 * j4 + 2], a[4 * j4 + 3]);
+              ph[2 * j4] = relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
+              ph[2 * j4 + 1] = relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
+            }
+            if (masks) {  // 16 ReLU gates of this slice = one half of gate word col / 32
+              uint32_t bits = 0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) bits |= (a[j] > 0.f ? 1u : 0u) << j;
+              reinterpret_cast<unsigned short*>(masks)[2 * mask_index(tile, layer, row, 0, (int)(col >> 5)) + ((col >> 4) & 1)] = (unsigned short)bits;
+            }
+            if (layer == NERFW_LAYERS - 1) {
+              const float4* w4 = reinterpret_cast<const float4*>(vec + V_DENW + col);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 ww = w4[j4];
+                sig = fmaf(fmaxf(a[4 * j4], 0.f), ww.x, sig); sig = fmaf(fmaxf(a[4 * j4 + 1], 0.f), ww.y, sig);
+                sig = fmaf(fmaxf(a[4 * j4 + 2], 0.f), ww.z, sig); sig = fmaf(fmaxf(a[4 * j4 + 3], 0.f), ww.w, sig);
+              }
+            }
+            tmem_st8(tlane + COL_AHI + (col >> 1), ph);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive_warp(&a_kb[kb]);
+            if (tid == 0 && kb == 0) NERFW_STAMP(16 + layer * 8);
+            if (tid == 0 && kb == 3) NERFW_STAMP(17 + layer * 8);
+          }
+        }
+      } else
       for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
@@ -364,6 +479,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         if (masks) masks[mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))] = bits;
       }
       tc_fence_before();
+      if constexpr (!X3) mbar_arrive_warp(acc_free);   // the next tile's layer 0 may start
       if (cq != 0) rgb_part[cq * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
       named_bar_sync(1, F_EPI_THREADS);
       if (cq == 0 && live) {
@@ -492,11 +608,14 @@ int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSou
   int64_t ntiles = ceil_div64(n_total, tc::TM);
   int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  const int dbg = getenv("NERFW_FWD_SKIP_WEIGHTS") ? 1 : 0;  // profiling switch: time the kernel without L2 weight traffic
+  long long* timeline = nullptr;                              // profiling switch: device pointer (decimal) to 128 int64 slots
+  if (const char* t = getenv("NERFW_FWD_TIMELINE")) timeline = reinterpret_cast<long long*>(strtoull(t, nullptr, 10));
   const float4* ao = reinterpret_cast<const float4*>(app_off);
   if (x3)
-    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks));
+    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks), dbg, timeline);
   else
-    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks));
+    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks), dbg, timeline);
   NERFW_LAUNCHED();
   return NERFW_OK;
 }
