@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   uint64_t* empty = full + NSTAGES;
   uint64_t* acc_full = empty + NSTAGES;
   uint64_t* a_ready = acc_full + 1;
-  // bf16 mode only: per-K-block operand barriers, accumulator-free and encodings-ready barriers (see the epilogue)
+  // per-K-block operand barriers, accumulator-free and encodings-ready barriers (one arrival per epilogue warp)
   uint64_t* a_kb = a_ready + 1;
   uint64_t* acc_free = a_kb + 4;
   uint64_t* pe_ready = acc_free + 1;
@@ -144,7 +144,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   if (warp == F_PRODUCER_WARP && lane == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(a_ready, F_EPI_WARPS);   // one arrival per epilogue warp
     for (int i = 0; i < 4; ++i) mbar_init(&a_kb[i], F_EPI_WARPS);
     mbar_init(acc_free, F_EPI_WARPS);
     mbar_init(pe_ready, F_EPI_WARPS);
@@ -192,7 +191,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     // ===================== MMA issuer =====================
     if (lane == 0) {
       Pipe p;
-      uint32_t ar_phase = 0;
       const uint32_t idesc256 = idesc_bf16(128, 256), idesc128 = idesc_bf16(128, 128);
       const uint32_t ring = smem_u32(sm + SM_RING);
       const uint32_t d_acc = tmem + COL_ACC;
@@ -228,69 +226,45 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       };
       const uint64_t pex_hi = smem_desc_sw128(smem_u32(sm + SM_PEX_HI)), pex_lo = smem_desc_sw128(smem_u32(sm + SM_PEX_LO));
       const uint64_t ped_hi = smem_desc_sw128(smem_u32(sm + SM_PED_HI)), ped_lo = smem_desc_sw128(smem_u32(sm + SM_PED_LO));
-      auto wait_a = [&]() {
-        mbar_wait(a_ready, ar_phase);
-        ar_phase ^= 1;
+      // The epilogue frees the accumulator as soon as it sits in registers and publishes the next A operand one 64-wide
+      // K block at a time, so the MMAs of layer l+1 start while most of epilogue l is still running.
+      uint32_t ph_free = 0, ph_pe = 0, ph_kb = 0;
+      auto wait_bar = [&](uint64_t* bar, uint32_t phase) {
+        mbar_wait(bar, phase);
         tc_fence_after();
       };
-      if constexpr (!X3) {
-        // bf16 mode: the epilogue frees the accumulator as soon as it sits in registers and publishes the next A operand
-        // one 64-wide K block at a time, so the MMAs of layer l+1 start while most of epilogue l is still running.
-        uint32_t ph_free = 0, ph_pe = 0, ph_kb = 0;
-        auto wait_bar = [&](uint64_t* bar, uint32_t phase) {
-          mbar_wait(bar, phase);
-          tc_fence_after();
-        };
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-          wait_bar(pe_ready, ph_pe);
-          ph_pe ^= 1;
-          NERFW_STAMP(0);
-          for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
-            wait_bar(acc_free, ph_free);
-            ph_free ^= 1;
-            NERFW_STAMP(10 + layer * 8);       // accumulator free seen by the MMA thread
-            if (layer == 0) {
-              kblock(false, pex_hi, 0, idesc256, 4, true);
-            } else {
-              for (int kb = 0; kb < 4; ++kb) {
-                wait_bar(&a_kb[kb], ph_kb);
-                if (kb == 0) NERFW_STAMP(11 + layer * 8);   // first operand K block seen
-                if (kb == 3) NERFW_STAMP(12 + layer * 8);   // last operand K block seen
-                kblock(true, tmem + COL_AHI + 32 * kb, 0, idesc256, 4, kb == 0);
-              }
-              ph_kb ^= 1;
-              if (layer == NERFW_SKIP) kblock(false, pex_hi, 0, idesc256, 4, false);
-            }
-            mma_commit(acc_full);
-            NERFW_STAMP(13 + layer * 8);       // all MMAs of the layer issued
-          }
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        wait_bar(pe_ready, ph_pe);
+        ph_pe ^= 1;
+        NERFW_STAMP(0);
+        for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
           wait_bar(acc_free, ph_free);
           ph_free ^= 1;
-          for (int kb = 0; kb < 4; ++kb) {
-            wait_bar(&a_kb[kb], ph_kb);
-            kblock(true, tmem + COL_AHI + 32 * kb, 0, idesc128, 4, kb == 0);
-          }
-          ph_kb ^= 1;
-          kblock(false, ped_hi, 0, idesc128, 2, false);
-          mma_commit(acc_full);
-        }
-      } else {
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
-          wait_a();
+          NERFW_STAMP(10 + layer * 8);       // accumulator free seen by the MMA thread
           if (layer == 0) {
             kblock(false, pex_hi, pex_lo, idesc256, 4, true);
           } else {
-            for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc256, 4, kb == 0);
+            for (int kb = 0; kb < 4; ++kb) {
+              wait_bar(&a_kb[kb], ph_kb);
+              if (kb == 0) NERFW_STAMP(11 + layer * 8);   // first operand K block seen
+              if (kb == 3) NERFW_STAMP(12 + layer * 8);   // last operand K block seen
+              kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc256, 4, kb == 0);
+            }
+            ph_kb ^= 1;
             if (layer == NERFW_SKIP) kblock(false, pex_hi, pex_lo, idesc256, 4, false);
           }
           mma_commit(acc_full);
+          NERFW_STAMP(13 + layer * 8);       // all MMAs of the layer issued
         }
-        wait_a();
-        for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, kb == 0, dir_split);
+        wait_bar(acc_free, ph_free);
+        ph_free ^= 1;
+        for (int kb = 0; kb < 4; ++kb) {
+          wait_bar(&a_kb[kb], ph_kb);
+          kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, kb == 0, dir_split);
+        }
+        ph_kb ^= 1;
         kblock(false, ped_hi, ped_lo, idesc128, 2, false, dir_split);
         mma_commit(acc_full);
-      }
       }
     }
   } else {
@@ -302,159 +276,115 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     uint8_t* pex_hi = sm + SM_PEX_HI;
     uint8_t* pex_lo = sm + SM_PEX_LO;
     uint8_t* ped_hi = sm + SM_PED_HI;
-    if constexpr (!X3) mbar_arrive_warp(acc_free);   // the accumulator starts out free
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t s = tile * TM + row;
-      const bool live = s < n_total;
-      // ---- encodings: quarter 0 / 1 -> position features 0..31 / 32..63, quarter 2 -> the direction tile ----
-      {
+    mbar_arrive_warp(acc_free);   // the accumulator starts out free
+    // ---- encodings (src/models.py:35-44).  Column quarters 0 / 1 write position features 0..31 / 32..63 of a tile,
+    // quarter 2 its direction tile.  They are not on the MMA critical path: the position tile of the NEXT sample tile and
+    // the direction tile of the current one are filled in between two trunk epilogues, once the skip layer has consumed
+    // the position tile, while the tensor pipe works on layer 6.
+    auto encode_pos = [&](int64_t t) {
+      if (cq < 2) {
+        const int64_t sr = t * TM + row;
         float x[3] = {0.f, 0.f, 0.f};
-        if (live) src.position(s, x);
+        if (sr < n_total) src.position(sr, x);
         float v[32];
         if (cq == 0) {
           pos_features32<0, !X3>(x, v);
           store_features32<X3>(pex_hi, pex_lo, row, 0, v);
-        } else if (cq == 1) {
+        } else {
           pos_features32<1, !X3>(x, v);
           store_features32<X3>(pex_hi, pex_lo, row, 32, v);
-        } else if (cq == 2) {
-          float d[3] = {0.f, 0.f, 0.f};
-          if (live) src.direction(s, d);
-          dir_features32<!X3>(d, v);
-          if (dir_split) store_features32<true>(ped_hi, sm + SM_PED_LO, row, 0, v);
-          else store_features32<false>(ped_hi, ped_hi, row, 0, v);
         }
       }
       fence_proxy_async_smem();
-      if constexpr (X3) mbar_arrive_warp(a_ready); else mbar_arrive_warp(pe_ready);
-
+      mbar_arrive_warp(pe_ready);
+    };
+    auto encode_dir = [&](int64_t t) {
+      if (cq == 2) {
+        const int64_t sr = t * TM + row;
+        float d[3] = {0.f, 0.f, 0.f};
+        if (sr < n_total) src.direction(sr, d);
+        float v[32];
+        dir_features32<!X3>(d, v);
+        if (dir_split) store_features32<true>(ped_hi, sm + SM_PED_LO, row, 0, v);
+        else store_features32<false>(ped_hi, ped_hi, row, 0, v);
+        fence_proxy_async_smem();   // ordered before this warp's later a_kb arrivals, which the MMA thread waits on
+      }
+    };
+    if ((int64_t)blockIdx.x < ntiles) encode_pos(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t s = tile * TM + row;
+      const bool live = s < n_total;
       // ---- trunk epilogues: acc -> bias, ReLU -> bf16 (hi[,lo]) -> next layer's A operand in TMEM ----
       float sig = 0.f;
-      if constexpr (!X3) {
-        // bf16 mode.  Thread <-> (row, 16-column slice cq of every 64-wide K block).  All 64 accumulator values are pulled
-        // into registers first and the accumulator is released; the four slices are then finished and published one K
-        // block at a time, so the next layer's MMAs overlap with three quarters of this epilogue.
-        for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
-          mbar_wait(acc_full, acc_phase);
-          acc_phase ^= 1;
-          tc_fence_after();
-          if (tid == 0) NERFW_STAMP(14 + layer * 8);   // accumulator complete seen by the epilogue
-          const float* bias = vec + V_PTSB + layer * 256;
-          uint32_t r[4][16];
-#pragma unroll
-          for (int kb = 0; kb < 4; ++kb) tmem_ld16(tlane + COL_ACC + kb * 64 + cq * 16, r[kb]);
-          tmem_wait_ld();
-          tc_fence_before();
-          mbar_arrive_warp(acc_free);
-          if (tid == 0) NERFW_STAMP(15 + layer * 8);   // accumulator in registers
-#pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            const uint32_t col = kb * 64 + cq * 16;
-            const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-            uint32_t ph[8];
-            float a[16];
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 bb = b4[j4];
-              unpack2f(add2(pack2(r[kb][4 * j4], r[kb][4 * j4 + 1]), pack2f(bb.x, bb.y)), a[4 * j4], a[4 * j4 + 1]);
-              unpack2f(add2(pack2(r[kb][4 * j4 + 2], r[kb][4 * j4 + 3]), pack2f(bb.z, bb.w)), a[4 * j4 + 2], a[4 * j4 + 3]);
-              ph[2 * j4] = relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
-              ph[2 * j4 + 1] = relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
-            }
-            if (masks) {  // 16 ReLU gates of this slice = one half of gate word col / 32
-              uint32_t bits = 0;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) bits |= (a[j] > 0.f ? 1u : 0u) << j;
-              reinterpret_cast<unsigned short*>(masks)[2 * mask_index(tile, layer, row, 0, (int)(col >> 5)) + ((col >> 4) & 1)] = (unsigned short)bits;
-            }
-            if (layer == NERFW_LAYERS - 1) {
-              const float4* w4 = reinterpret_cast<const float4*>(vec + V_DENW + col);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 ww = w4[j4];
-                sig = fmaf(fmaxf(a[4 * j4], 0.f), ww.x, sig); sig = fmaf(fmaxf(a[4 * j4 + 1], 0.f), ww.y, sig);
-                sig = fmaf(fmaxf(a[4 * j4 + 2], 0.f), ww.z, sig); sig = fmaf(fmaxf(a[4 * j4 + 3], 0.f), ww.w, sig);
-              }
-            }
-            tmem_st8(tlane + COL_AHI + (col >> 1), ph);
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive_warp(&a_kb[kb]);
-            if (tid == 0 && kb == 0) NERFW_STAMP(16 + layer * 8);
-            if (tid == 0 && kb == 3) NERFW_STAMP(17 + layer * 8);
-          }
-        }
-      } else
+      // Thread <-> (row, 16-column slice cq of every 64-wide K block).  All 64 accumulator values are pulled into
+      // registers first and the accumulator is released; the four slices are then finished and published one K block at
+      // a time, so the next layer's MMAs overlap with three quarters of this epilogue.
       for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        if (tid == 0) NERFW_STAMP(14 + layer * 8);   // accumulator complete seen by the epilogue
         const float* bias = vec + V_PTSB + layer * 256;
-#pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-          const uint32_t col = cq * 64 + q * 32;
-          uint32_t r[32];
-          tmem_ld32(tlane + COL_ACC + col, r);
-          tmem_wait_ld();
+        // inference: the direction layer consumes A_hi only
+        const bool want_lo = X3 && (layer != NERFW_LAYERS - 1 || dir_split);
+        uint32_t r[4][16];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) tmem_ld16(tlane + COL_ACC + kb * 64 + cq * 16, r[kb]);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_warp(acc_free);
+        if (tid == 0) NERFW_STAMP(15 + layer * 8);   // accumulator in registers
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint32_t col = kb * 64 + cq * 16;
           const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-          uint32_t ph[16];
-          const bool plain = !X3 && !masks && layer != NERFW_LAYERS - 1;  // warp-uniform
-          if (plain) {
-            // bf16 fast path: one FADD2 + one F2FP.RELU per two columns
+          uint32_t ph[8];
+          float a[16];
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4];
-              float a0, a1, a2, a3;
-              unpack2f(add2(pack2(r[4 * j4], r[4 * j4 + 1]), pack2f(bb.x, bb.y)), a0, a1);
-              unpack2f(add2(pack2(r[4 * j4 + 2], r[4 * j4 + 3]), pack2f(bb.z, bb.w)), a2, a3);
-              ph[2 * j4] = relu_pack_bf16x2(a0, a1);
-              ph[2 * j4 + 1] = relu_pack_bf16x2(a2, a3);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = b4[j4];
+            unpack2f(add2(pack2(r[kb][4 * j4], r[kb][4 * j4 + 1]), pack2f(bb.x, bb.y)), a[4 * j4], a[4 * j4 + 1]);
+            unpack2f(add2(pack2(r[kb][4 * j4 + 2], r[kb][4 * j4 + 3]), pack2f(bb.z, bb.w)), a[4 * j4 + 2], a[4 * j4 + 3]);
+            ph[2 * j4] = relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
+            ph[2 * j4 + 1] = relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
+          }
+          tmem_st8(tlane + COL_AHI + (col >> 1), ph);
+          if (want_lo) {  // lo = bf16(relu(a) - hi)
+            uint32_t pl[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float l0v, l1v;
+              unpack2f(sub2(pack2f(fmaxf(a[2 * j], 0.f), fmaxf(a[2 * j + 1], 0.f)), pack2(ph[j] << 16, ph[j] & 0xffff0000u)), l0v, l1v);
+              pl[j] = pack_bf16x2(l0v, l1v);
             }
-            tmem_st16(tlane + COL_AHI + (col >> 1), ph);
-          } else {
-            float v[32];
+            tmem_st8(tlane + COL_ALO + (col >> 1), pl);
+          }
+          if (masks) {  // 16 ReLU gates of this slice = one half of gate word col / 32
+            uint32_t bits = 0;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4];
-              float a0, a1, a2, a3;
-              unpack2f(add2(pack2(r[4 * j4], r[4 * j4 + 1]), pack2f(bb.x, bb.y)), a0, a1);
-              unpack2f(add2(pack2(r[4 * j4 + 2], r[4 * j4 + 3]), pack2f(bb.z, bb.w)), a2, a3);
-              v[4 * j4] = fmaxf(a0, 0.f); v[4 * j4 + 1] = fmaxf(a1, 0.f);
-              v[4 * j4 + 2] = fmaxf(a2, 0.f); v[4 * j4 + 3] = fmaxf(a3, 0.f);
-            }
-            if (masks) {  // ReLU gates for the backward pass (training): bit j <-> column col + j
-              uint32_t bits = 0;
+            for (int j = 0; j < 16; ++j) bits |= (a[j] > 0.f ? 1u : 0u) << j;
+            reinterpret_cast<unsigned short*>(masks)[2 * mask_index(tile, layer, row, 0, (int)(col >> 5)) + ((col >> 4) & 1)] = (unsigned short)bits;
+          }
+          if (layer == NERFW_LAYERS - 1) {
+            const float4* w4 = reinterpret_cast<const float4*>(vec + V_DENW + col);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-              masks[mask_index(tile, layer, row, 0, (int)(col >> 5))] = bits;
-            }
-            if (layer == NERFW_LAYERS - 1) {
-              const float4* w4 = reinterpret_cast<const float4*>(vec + V_DENW + col);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 ww = w4[j4];
-                sig = fmaf(v[4 * j4], ww.x, sig); sig = fmaf(v[4 * j4 + 1], ww.y, sig);
-                sig = fmaf(v[4 * j4 + 2], ww.z, sig); sig = fmaf(v[4 * j4 + 3], ww.w, sig);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            tmem_st16(tlane + COL_AHI + (col >> 1), ph);
-            if (X3 && (layer != NERFW_LAYERS - 1 || dir_split)) {  // inference: the direction layer consumes A_hi only
-              uint32_t pl[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float l0v, l1v;
-                unpack2f(sub2(pack2f(v[2 * j], v[2 * j + 1]), pack2(ph[j] << 16, ph[j] & 0xffff0000u)), l0v, l1v);
-                pl[j] = pack_bf16x2(l0v, l1v);
-              }
-              tmem_st16(tlane + COL_ALO + (col >> 1), pl);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 ww = w4[j4];
+              sig = fmaf(fmaxf(a[4 * j4], 0.f), ww.x, sig); sig = fmaf(fmaxf(a[4 * j4 + 1], 0.f), ww.y, sig);
+              sig = fmaf(fmaxf(a[4 * j4 + 2], 0.f), ww.z, sig); sig = fmaf(fmaxf(a[4 * j4 + 3], 0.f), ww.w, sig);
             }
           }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive_warp(&a_kb[kb]);
+          if (tid == 0 && kb == 0) NERFW_STAMP(16 + layer * 8);
+          if (tid == 0 && kb == 3) NERFW_STAMP(17 + layer * 8);
         }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive_warp(a_ready);
+        if (layer == NERFW_SKIP + 1) {
+          encode_dir(tile);
+          if (tile + gridDim.x < ntiles) encode_pos(tile + gridDim.x);
+          if (tid == 0) NERFW_STAMP(90);   // encodings written
+        }
       }
       sig_part[cq * TM + row] = sig;
 
@@ -462,12 +392,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       mbar_wait(acc_full, acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
+      if (tid == 0) NERFW_STAMP(91);   // direction-layer accumulator complete seen
       float p3[3] = {0.f, 0.f, 0.f};
       {
         const uint32_t col = cq * 32;
         uint32_t r[32];
         tmem_ld32(tlane + COL_ACC + col, r);
         tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_warp(acc_free);   // the next tile's layer 0 may start
+        if (tid == 0) NERFW_STAMP(92);
         uint32_t bits = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -478,8 +412,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         }
         if (masks) masks[mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))] = bits;
       }
-      tc_fence_before();
-      if constexpr (!X3) mbar_arrive_warp(acc_free);   // the next tile's layer 0 may start
       if (cq != 0) rgb_part[cq * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
       named_bar_sync(1, F_EPI_THREADS);
       if (cq == 0 && live) {
@@ -494,6 +426,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         o.w = fmaxf(sg, 0.f);
         raw[s] = o;
       }
+      if (tid == 0) NERFW_STAMP(93);   // tile written
     }
   }
   // ---- teardown ----

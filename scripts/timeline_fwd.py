@@ -7,6 +7,7 @@ from config import Config
 from nerfw import ops
 m = nerfw.NeRF(Config()); m.load_state_dict(orc.make_state_dict(0)); m = m.cuda()
 b, n = 40000, 192
+MODE = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 g = torch.Generator(device="cuda").manual_seed(1)
 o = torch.randn(b, 3, device="cuda", generator=g)
 d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda", generator=g), dim=-1)
@@ -15,9 +16,9 @@ names, tensors = m.kernel_params()
 params = {k: t.detach() for k, t in zip(names, tensors)}
 packed = m.packed_weights(names, tensors)
 tl = torch.zeros(128, dtype=torch.int64, device="cuda")
-ops.mlp_fwd(params, packed, o, d, z, None, 2)
+ops.mlp_fwd(params, packed, o, d, z, None, MODE)
 os.environ["NERFW_FWD_TIMELINE"] = str(tl.data_ptr())
-ops.mlp_fwd(params, packed, o, d, z, None, 2)
+ops.mlp_fwd(params, packed, o, d, z, None, MODE)
 torch.cuda.synchronize()
 t = tl.cpu().tolist()
 t0 = t[0]
@@ -26,3 +27,5 @@ print("cycles relative to pe_ready seen by the MMA thread (tile 3 of CTA 0)")
 for layer in range(8):
     row = [(names[i], t[10 + layer * 8 + i] - t0 if t[10 + layer * 8 + i] else None) for i in range(8)]
     print(f"layer {layer}: " + "  ".join(f"{k}={v}" for k, v in row))
+for slot, name in ((90, "epi: encodings for next tile written"), (91, "epi: dir acc complete seen"), (92, "epi: dir acc in regs"), (93, "epi: tile written")):
+    print(f"{name}: {t[slot] - t0 if t[slot] else None}")
