@@ -129,8 +129,19 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + SM_BAR);
-  uint64_t* empty = full + NSTAGES;
-  uint64_t* acc_full = empty + NSTAGES;
+  // bf16 mode has no lo operand tiles: that space is a fifth ring stage (deeper weight prefetch across the epilogue gaps)
+  constexpr int STAGES = X3 ? NSTAGES : NSTAGES + 1;
+  constexpr uint32_t RING = X3 ? SM_RING : SM_RING - BIG_CHUNK;
+  constexpr uint32_t PED_HI = X3 ? SM_PED_HI : SM_PEX_LO;
+  struct RingPipe {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance() {
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  };
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
   uint64_t* a_ready = acc_full + 1;
   // per-K-block operand barriers, accumulator-free and encodings-ready barriers (one arrival per epilogue warp)
   uint64_t* a_kb = a_ready + 1;
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   float4* rgb_part = reinterpret_cast<float4*>(sm + SM_RGB);
 
   if (warp == F_PRODUCER_WARP && lane == 0) {
-    for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&a_kb[i], F_EPI_WARPS);
     mbar_init(acc_free, F_EPI_WARPS);
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   if (warp == F_PRODUCER_WARP) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      Pipe p;
+      RingPipe p;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         size_t off = 0;
         for (int i = 0; i < N_CHUNKS; ++i) {
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
               mbar_arrive(&full[p.stage]);   // profiling only: reuse whatever the stage holds (results are wrong)
             } else {
               mbar_arrive_expect_tx(&full[p.stage], sz);
-              bulk_g2s(sm + SM_RING + p.stage * BIG_CHUNK, packed + off + (size_t)v * sz, sz, &full[p.stage]);
+              bulk_g2s(sm + RING + p.stage * BIG_CHUNK, packed + off + (size_t)v * sz, sz, &full[p.stage]);
             }
             p.advance();
           }
@@ -190,9 +201,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   } else if (warp == F_MMA_WARP) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      Pipe p;
+      RingPipe p;
       const uint32_t idesc256 = idesc_bf16(128, 256), idesc128 = idesc_bf16(128, 128);
-      const uint32_t ring = smem_u32(sm + SM_RING);
+      const uint32_t ring = smem_u32(sm + RING);
       const uint32_t d_acc = tmem + COL_ACC;
       // one 64-wide K block: A (hi[,lo]) x W chunk (hi[,lo]); a_* are either TMEM addresses (TS) or smem descs (SS)
       auto kblock = [&](bool from_tmem, uint64_t a_hi, uint64_t a_lo, uint32_t idesc, int ksteps, bool first, bool split = X3) {
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         }
       };
       const uint64_t pex_hi = smem_desc_sw128(smem_u32(sm + SM_PEX_HI)), pex_lo = smem_desc_sw128(smem_u32(sm + SM_PEX_LO));
-      const uint64_t ped_hi = smem_desc_sw128(smem_u32(sm + SM_PED_HI)), ped_lo = smem_desc_sw128(smem_u32(sm + SM_PED_LO));
+      const uint64_t ped_hi = smem_desc_sw128(smem_u32(sm + PED_HI)), ped_lo = smem_desc_sw128(smem_u32(sm + SM_PED_LO));
       // The epilogue frees the accumulator as soon as it sits in registers and publishes the next A operand one 64-wide
       // K block at a time, so the MMAs of layer l+1 start while most of epilogue l is still running.
       uint32_t ph_free = 0, ph_pe = 0, ph_kb = 0;
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     uint32_t acc_phase = 0;
     uint8_t* pex_hi = sm + SM_PEX_HI;
     uint8_t* pex_lo = sm + SM_PEX_LO;
-    uint8_t* ped_hi = sm + SM_PED_HI;
+    uint8_t* ped_hi = sm + PED_HI;
     mbar_arrive_warp(acc_free);   // the accumulator starts out free
     // ---- encodings (src/models.py:35-44).  Column quarters 0 / 1 write position features 0..31 / 32..63 of a tile,
     // quarter 2 its direction tile.  They are not on the MMA critical path: the position tile of the NEXT sample tile and
