@@ -160,6 +160,36 @@ def test_sample_pdf_thread_per_ray_variant_bit_exact(golden, monkeypatch):
     assert torch.equal(a, b)
 
 
+def test_sample_pdf_merge_path_equals_general_path(oracle, monkeypatch):
+    """The merge path (sorted u: no searches) and the general search + sort path return the same bits; rays whose u is
+    not sorted (rand outside [0,1)), whose depths are unsorted or whose weights are negative fall back inside the kernel."""
+    from nerfw import ops
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    b, n, ni = 20000, 64, 128
+    z = torch.sort(torch.rand(b, n, device="cuda", generator=gen) * 4 + 2, dim=-1).values
+    w = torch.rand(b, n, device="cuda", generator=gen) ** 8
+    w[:500] = 0.0
+    w[500:1000, 5:] = 0.0                    # one occupied bin: most cdf entries equal
+    u = torch.rand(b, ni, device="cuda", generator=gen)
+    u[1000:1500] = u[1000:1500] * 3.0        # unsorted u -> in-kernel fallback
+    u[1500:1600] = 0.0
+    u[1600:1700] = 1.0 - 2.0 ** -24
+    z[1700:1800] = z[1700:1800].flip(-1)     # unsorted depths -> fallback
+    w[1800:1900, ::7] = -0.5                 # non-monotone cdf -> fallback
+    got, aux = ops.sample_pdf(z, w, ni, u, want_aux=True)
+    monkeypatch.setenv("NERFW_RESAMPLE_GENERAL", "1")
+    want, aux_w = ops.sample_pdf(z, w, ni, u, want_aux=True)
+    monkeypatch.delenv("NERFW_RESAMPLE_GENERAL")
+    assert torch.equal(got, want)
+    assert torch.equal(aux["inds"], aux_w["inds"]) and torch.equal(aux["z_fine"], aux_w["z_fine"])
+    # and both equal the oracle where its searchsorted is well defined (sorted cdf)
+    sel = torch.cat([torch.arange(0, 1700), torch.arange(1900, 4000)])
+    o = torch.zeros(len(sel), 3)
+    zw, _, oaux = oracle.resample_pdf(o, o, z[sel].cpu(), w[sel].cpu(), ni, u_rand=u[sel].cpu(), return_aux=True)
+    assert torch.equal(aux["inds"][sel].cpu(), oaux["inds"])
+    assert torch.equal(got[sel].cpu(), zw)
+
+
 def test_sample_pdf_full_size_properties():
     """800x800 rays x (64 -> +128): sortedness, range and multiset-preservation of the coarse depths."""
     from nerfw import ops
