@@ -17,4 +17,4 @@ for _ in range(10):
     out = ops.sample_pdf(z, w, ni, u)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
-print(f"NERFW_RESAMPLE_WARP={os.environ.get('NERFW_RESAMPLE_WARP')}: {ms:.3f} ms per call, {b * (3 * n + 2 * ni) * 4 / ms / 1e6:.0f} GB/s algorithmic")
+print(f"sample_pdf general={os.environ.get('NERFW_RESAMPLE_GENERAL')}: {ms:.3f} ms per call, {b * (3 * n + 2 * ni) * 4 / ms / 1e6:.0f} GB/s algorithmic")

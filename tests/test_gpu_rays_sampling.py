@@ -138,28 +138,6 @@ def test_sample_pdf_vs_oracle(oracle, n, ni, b):
         assert torch.equal(pts.cpu(), pw)
 
 
-def test_sample_pdf_thread_per_ray_variant_bit_exact(golden, monkeypatch):
-    """The opt-in thread-per-ray kernel (NERFW_RESAMPLE_TPR=1) returns the same bits as the default kernel."""
-    from nerfw import ops
-    g = golden("resample")
-    z = torch.from_numpy(g["z_gen"]).cuda()
-    w = torch.from_numpy(g["w_gen"]).cuda()
-    u = torch.from_numpy(g["u_rand_gen"]).cuda()
-    want, aux_w = ops.sample_pdf(z, w, 128, u, want_aux=True)
-    monkeypatch.setenv("NERFW_RESAMPLE_TPR", "1")
-    got, aux = ops.sample_pdf(z, w, 128, u, want_aux=True)
-    assert torch.equal(got, want) and torch.equal(aux["inds"], aux_w["inds"]) and torch.equal(aux["cdf"], aux_w["cdf"])
-    assert torch.equal(got.cpu(), torch.from_numpy(g["out_gen"]))
-    gen = torch.Generator(device="cuda").manual_seed(8)
-    z2 = torch.sort(torch.rand(1000, 96, device="cuda", generator=gen) * 4 + 2, dim=-1).values
-    w2 = torch.rand(1000, 96, device="cuda", generator=gen) ** 6
-    u2 = torch.rand(1000, 100, device="cuda", generator=gen)
-    a = ops.sample_pdf(z2, w2, 100, u2)
-    monkeypatch.delenv("NERFW_RESAMPLE_TPR")
-    b = ops.sample_pdf(z2, w2, 100, u2)
-    assert torch.equal(a, b)
-
-
 def test_sample_pdf_merge_path_equals_general_path(oracle, monkeypatch):
     """The merge path (sorted u: no searches) and the general search + sort path return the same bits; rays whose u is
     not sorted (rand outside [0,1)), whose depths are unsorted or whose weights are negative fall back inside the kernel."""
