@@ -356,3 +356,81 @@ def selftest_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     with torch.cuda.device(a.device):
         check(lib().nerfw_selftest_umma(a.data_ptr(), b.data_ptr(), b.shape[0], a.shape[1], int(mode), d.data_ptr(), _stream()))
     return d
+
+
+# ---- depth-aware effects --------------------------------------------------------------------------
+def _u8c(x: torch.Tensor, name: str) -> torch.Tensor:
+    if x.dtype != torch.uint8 or not x.is_cuda:
+        raise ValueError(f"{name} must be a CUDA uint8 tensor")
+    return x.contiguous()
+
+
+def max_f32(x: torch.Tensor) -> torch.Tensor:
+    """Device scalar max(x) (depth.max() of src/post_processor.py:64,408,476); no host sync."""
+    x = _f32c(x, "x")
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().nerfw_max_f32(x.data_ptr(), x.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def fog(image: torch.Tensor, depth: torch.Tensor, depth_max: torch.Tensor, fog_start: float, power: float,
+        visibility: float, fog_color) -> torch.Tensor:
+    image = _u8c(image, "image")
+    depth = _f32c(depth, "depth")
+    n = depth.numel()
+    if image.numel() != 3 * n:
+        raise ValueError(f"image must hold 3 values per depth pixel, got {tuple(image.shape)} vs {tuple(depth.shape)}")
+    out = torch.empty_like(image)
+    color = (C.c_float * 3)(*[float(c) for c in fog_color])
+    with torch.cuda.device(depth.device):
+        check(lib().nerfw_fog(image.data_ptr(), depth.data_ptr(), depth_max.data_ptr(), n, float(fog_start), float(power),
+                              float(visibility), color, out.data_ptr(), _stream()))
+    return out
+
+
+def depth_edges(depth: torch.Tensor, depth_max: torch.Tensor, bilateral_d: int = 0, sigma_color: float = 75.0,
+                sigma_space: float = 75.0):
+    """-> (mag (H,W), mag_max (1,), filtered (H,W) or None)."""
+    depth = _f32c(depth, "depth")
+    if depth.dim() != 2:
+        raise ValueError(f"depth must be (H,W), got {tuple(depth.shape)}")
+    h, w = depth.shape
+    mag = torch.empty_like(depth)
+    mag_max = torch.empty(1, dtype=torch.float32, device=depth.device)
+    filtered = torch.empty_like(depth) if bilateral_d else None
+    with torch.cuda.device(depth.device):
+        check(lib().nerfw_depth_edges(depth.data_ptr(), depth_max.data_ptr(), h, w, int(bilateral_d), float(sigma_color),
+                                      float(sigma_space), _ptr(filtered), mag.data_ptr(), mag_max.data_ptr(), _stream()))
+    return mag, mag_max, filtered
+
+
+def toon(image: torch.Tensor, mag: torch.Tensor, mag_max: torch.Tensor, levels: int, edge_strength: float) -> torch.Tensor:
+    image = _u8c(image, "image")
+    h, w = mag.shape
+    if tuple(image.shape) != (h, w, 3):
+        raise ValueError(f"image must be ({h},{w},3), got {tuple(image.shape)}")
+    out = torch.empty_like(image)
+    with torch.cuda.device(image.device):
+        check(lib().nerfw_toon(image.data_ptr(), mag.data_ptr(), mag_max.data_ptr(), h, w, int(levels), float(edge_strength),
+                               out.data_ptr(), _stream()))
+    return out
+
+
+def hologram(image: torch.Tensor, mag, mag_max, row_scale: torch.Tensor, col_hits, noise) -> torch.Tensor:
+    image = _u8c(image, "image")
+    h, w, _ = image.shape
+    row_scale = _f32c(row_scale, "row_scale")
+    if row_scale.numel() != h:
+        raise ValueError(f"row_scale must have {h} entries")
+    if col_hits is not None and (col_hits.dtype != torch.int32 or col_hits.numel() != w):
+        raise ValueError(f"col_hits must be int32 with {w} entries")
+    if noise is not None:
+        noise = _f32c(noise, "noise")
+        if tuple(noise.shape) != (h, w, 3):
+            raise ValueError(f"noise must be ({h},{w},3)")
+    out = torch.empty_like(image)
+    with torch.cuda.device(image.device):
+        check(lib().nerfw_hologram(image.data_ptr(), _ptr(mag), _ptr(mag_max), row_scale.data_ptr(), _ptr(col_hits),
+                                   _ptr(noise), h, w, out.data_ptr(), _stream()))
+    return out

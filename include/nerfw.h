@@ -186,6 +186,39 @@ int nerfw_mse(const float* rgb, const float* target, int64_t n, float loss_scale
  * depth (n) -> uint8 by the min/max normalisation of :171-173 given dmin,dmax. */
 int nerfw_quantize_u8(const float* rgb, int64_t n_values, uint8_t* out, void* stream);
 
+/* ---- depth-aware effects on the device-resident fp32 depth (src/post_processor.py) -------------
+ * Images are uint8 (H,W,3) like the reference's effect inputs; depth is the renderer's fp32 (H,W) buffer, normalised
+ * inside the kernels exactly like the reference: depth / depth.max() when depth.max() > 1 (:64-66, :405-408,
+ * :473-477).  All pointers are device pointers unless named *_host. */
+
+/* out[0] = max(x[0..n)) (depth.max()). */
+int nerfw_max_f32(const float* x, int64_t n, float* out, void* stream);
+
+/* _effect_fog (src/post_processor.py:451-493): f = clip(max(d_norm - fog_start, 0) / (1 - fog_start), 0, 1) ** power *
+ * visibility; out = clip(image * f + fog_color * (1 - f), 0, 255) truncated to uint8.  depth_max: device scalar from
+ * nerfw_max_f32.  Reference constants: fog_start 0.0, power 3.0, visibility 0.3, fog_color (255,255,255). */
+int nerfw_fog(const uint8_t* image, const float* depth, const float* depth_max, int64_t n_pixels, float fog_start,
+              float power, float visibility, const float* fog_color_host, uint8_t* out, void* stream);
+
+/* Depth-edge detector shared by _effect_toon (:62-78: cv2.bilateralFilter(depth_norm, 9, 75, 75) then Sobel) and
+ * _effect_hologram (:402-419: Sobel on depth_norm): mag = sqrt(Sobel_x^2 + Sobel_y^2) (ksize 3, BORDER_REFLECT_101),
+ * mag_max[0] = max(mag).  bilateral_d = 0: no pre-filter (`filtered` may be NULL); otherwise the filtered normalised
+ * depth is written to `filtered` (H,W). */
+int nerfw_depth_edges(const float* depth, const float* depth_max, int height, int width, int bilateral_d,
+                      float sigma_color, float sigma_space, float* filtered, float* mag, float* mag_max, void* stream);
+
+/* _effect_toon (:64-102) with depth: colours floor(img/255*levels)/levels*255, multiplied by (1 - edge_strength * e),
+ * e = 3x3 dilation of (mag / mag_max > 0.05). */
+int nerfw_toon(const uint8_t* image, const float* mag, const float* mag_max, int height, int width, int levels,
+               float edge_strength, uint8_t* out, void* stream);
+
+/* _effect_hologram (:373-449): ((img/255) * (0.8,1.0,0.2) * row_scale[y] + (mag/mag_max) * (0.1,0.6,0.3) + noise),
+ * x1.5 once per interference line covering column x (col_hits[x]), clip(x*255) truncated to uint8.  row_scale (H) is
+ * the scanline table of :385-393; noise (H,W,3), col_hits (W) and mag/mag_max may be NULL.  The reference draws noise
+ * and line positions from numpy's global RNG; here the caller supplies them. */
+int nerfw_hologram(const uint8_t* image, const float* mag, const float* mag_max, const float* row_scale,
+                   const int* col_hits, const float* noise, int height, int width, uint8_t* out, void* stream);
+
 /* Primitive self-test (tests only): D (128,n) fp32 = A (128,k) bf16 * B (n,k) bf16 ^T through one tcgen05 tile;
  * mode 0 = A from shared memory, 1 = A from tensor memory.  Pins the descriptor / swizzle / TMEM layouts. */
 int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream);
