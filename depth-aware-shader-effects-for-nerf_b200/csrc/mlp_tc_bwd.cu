@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
                                                                        const float4* __restrict__ d_raw, int64_t n_total,
                                                                        uint8_t* __restrict__ scratch,
                                                                        float* __restrict__ dl_acc,
-                                                                       const uint32_t* __restrict__ fwd_masks) {
+                                                                       const uint32_t* __restrict__ fwd_masks, int debug) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -260,44 +260,50 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
     // with the forward's gates the mask region of shared memory is free: 16 x 2 KB staging buffers for coalesced stores
     uint8_t* stage = fwd_masks ? sm + (warp < 8 ? SM1_MASK_A : SM1_MASK_B) + (warp & 7) * 2048 : nullptr;
     auto put = [&](uint8_t* tile_base, int block0, uint32_t col, const uint32_t (&p)[16]) {
+      if (debug & 4) return;   // profiling only (NERFW_WGRAD_DEBUG bit 2): no scratch stores
       if (stage) store_row32_staged(stage, tile_base, block0, quad * 32, lane, col, p);
       else store_row32(tile_base, block0, row, col, p);
     };
+    // ---- encodings (as in the bf16 forward kernel) of tile t into shared memory and, as wgrad operands of layer 0, of the
+    // skip part of layer 4 and of the direction layer, into its scratch tile.  Off the critical path: the encodings of
+    // the NEXT tile are produced during the dgrad phase of the current one, when the forward MMAs that read the shared
+    // tiles are long complete; the closing arrival on a_ready doubles as "operand TMEM columns free".
+    auto encode_tile = [&](int64_t t) {
+      const int64_t sr = t * TM + row;
+      float x[3] = {0.f, 0.f, 0.f};
+      if (sr < n_total && cq < 2) src.position(sr, x);
+      float v[32];
+      if (cq == 0) {
+        pos_features32<0, true>(x, v);
+        store_features32<false>(pex, pex, row, 0, v);
+      } else if (cq == 1) {
+        pos_features32<1, true>(x, v);
+        store_features32<false>(pex, pex, row, 32, v);
+      } else if (cq == 2) {
+        float d[3] = {0.f, 0.f, 0.f};
+        if (sr < n_total) src.direction(sr, d);
+        dir_features32<true>(d, v);
+        store_features32<false>(ped, ped, row, 0, v);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, P1_EPI_THREADS);
+      uint8_t* dst = scratch + (size_t)t * TILE_BYTES;
+      const int tt = warp * 32 + lane;  // 0..511
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int o = (tt + 512 * i) * 16;
+        *reinterpret_cast<uint4*>(dst + (size_t)XB_ENCX * BLK + o) = *reinterpret_cast<const uint4*>(pex + o);
+        *reinterpret_cast<uint4*>(dst + (size_t)XB_ENCD * BLK + o) = *reinterpret_cast<const uint4*>(ped + o);
+      }
+    };
+    if ((int64_t)blockIdx.x < ntiles) {
+      encode_tile(blockIdx.x);
+      mbar_arrive_warp(a_ready);
+    }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t s = tile * TM + row;
       const bool live = s < n_total;
       uint8_t* tsc = scratch + (size_t)tile * TILE_BYTES;
-      // ---- encodings (as in the bf16 forward kernel) ----
-      {
-        float x[3] = {0.f, 0.f, 0.f};
-        if (live) src.position(s, x);
-        float v[32];
-        if (cq == 0) {
-          pos_features32<0, true>(x, v);
-          store_features32<false>(pex, pex, row, 0, v);
-        } else if (cq == 1) {
-          pos_features32<1, true>(x, v);
-          store_features32<false>(pex, pex, row, 32, v);
-        } else if (cq == 2) {
-          float d[3] = {0.f, 0.f, 0.f};
-          if (live) src.direction(s, d);
-          dir_features32<true>(d, v);
-          store_features32<false>(ped, ped, row, 0, v);
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive_warp(a_ready);
-      // encodings -> scratch (wgrad operands of layer 0, the skip part of layer 4 and the direction layer)
-      named_bar_sync(1, P1_EPI_THREADS);
-      {
-        const int t = warp * 32 + lane;  // 0..511
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int o = (t + 512 * i) * 16;
-          *reinterpret_cast<uint4*>(tsc + (size_t)XB_ENCX * BLK + o) = *reinterpret_cast<const uint4*>(pex + o);
-          *reinterpret_cast<uint4*>(tsc + (size_t)XB_ENCD * BLK + o) = *reinterpret_cast<const uint4*>(ped + o);
-        }
-      }
 
       // ---- forward trunk epilogues: next A operand + activation tile (+ own ReLU gates when none were passed) ----
       float sig = 0.f;
@@ -307,14 +313,15 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         tc_fence_after();
         const float* bias = vec + V_PTSB + layer * 256;
         const bool plain = fwd_masks != nullptr && layer != NERFW_LAYERS - 1;  // warp-uniform
-#pragma unroll 1
+        uint32_t ph2[2][16];   // both 32-column halves: handed to the MMA thread first, stored to the scratch tile after
+#pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint32_t col = cq * 64 + q * 32;
+          uint32_t (&ph)[16] = ph2[q];
           uint32_t r[32];
           tmem_ld32(tlane + COL_ACC + col, r);
           tmem_wait_ld();
           const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-          uint32_t ph[16];
           if (plain) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -349,11 +356,12 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
             for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           }
           tmem_st16(tlane + COL_AHI + (col >> 1), ph);
-          put(tsc, XB_H(layer + 1), col, ph);
         }
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive_warp(a_ready);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) put(tsc, XB_H(layer + 1), cq * 64 + q * 32, ph2[q]);
       }
       sig_part[cq * TM + row] = sig;
 
@@ -364,12 +372,12 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
       float p3[3] = {0.f, 0.f, 0.f};
       uint32_t hmask;
       const uint32_t dcol = cq * 32;
+      uint32_t ph_hdt[16];
       {
         uint32_t r[32];
         tmem_ld32(tlane + COL_ACC + dcol, r);
         tmem_wait_ld();
         uint32_t bits = 0;
-        uint32_t ph[16];
         float hv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -379,8 +387,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
           for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv[j], vec[V_RGBW + c * 128 + dcol + j], p3[c]);
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(hv[2 * j] + appv[dcol + 2 * j], hv[2 * j + 1] + appv[dcol + 2 * j + 1]);
-        put(tsc, XB_HDT, dcol, ph);
+        for (int j = 0; j < 16; ++j) ph_hdt[j] = pack_bf16x2(hv[2 * j] + appv[dcol + 2 * j], hv[2 * j + 1] + appv[dcol + 2 * j + 1]);
         hmask = fwd_masks ? __ldg(fwd_masks + mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))) : bits;
       }
       tc_fence_before();
@@ -429,11 +436,12 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
           ph[j] = gate_pack(g0, g1, hmask, j);
         }
         tmem_st16(tlane + COL_AHI + (dcol >> 1), ph);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive_warp(a_ready);
         put(tsc, ZB_DIR, dcol, ph);
+        put(tsc, XB_HDT, dcol, ph_hdt);
       }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive_warp(a_ready);
       named_bar_sync(1, P1_EPI_THREADS);  // dsig_s visible to every column quarter
 
       // ---- dgrad epilogues, layer 7 down to 0: dZ_l = dH_{l+1} * gate_l ----
@@ -448,14 +456,15 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         tc_fence_after();
         const float ds = dsig_s[row];
         const uint64_t ds2 = pack2f(ds, ds);
+        uint32_t ph2[2][16];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint32_t col = cq * 64 + q * 32;
+          uint32_t (&ph)[16] = ph2[q];
           uint32_t r[32];
           tmem_ld32(tlane + COL_ACC + col, r);
           tmem_wait_ld();
           const uint32_t bits = fwd_masks ? gate[q] : mask_words(sm, l, row)[col >> 5];
-          uint32_t ph[16];
           if (l == NERFW_LAYERS - 1) {  // + density head: d sigma_pre * w_sigma
             const float2* w2 = reinterpret_cast<const float2*>(vec + V_DENW + col);
 #pragma unroll
@@ -470,7 +479,6 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
             for (int j = 0; j < 16; ++j) ph[j] = gate_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), bits, j);
           }
           if (l > 0) tmem_st16(tlane + COL_AHI + (col >> 1), ph);
-          put(tsc, ZB(l), col, ph);
         }
         if (l > 0) {
           tmem_wait_st();
@@ -478,7 +486,13 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
           mbar_arrive_warp(a_ready);
         } else {
           tc_fence_before();
+          // accumulator and operand columns are free and the next tile's encodings are in place (written below, during
+          // the dgrad phase): its layer 0 may start while this tile's last dZ block is still being stored
+          if (tile + gridDim.x < ntiles) mbar_arrive_warp(a_ready);
         }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) put(tsc, ZB(l), cq * 64 + q * 32, ph2[q]);
+        if (l == NERFW_LAYERS - 2 && tile + gridDim.x < ntiles) encode_tile(tile + gridDim.x);
       }
     }
   }
@@ -639,16 +653,21 @@ __global__ void __launch_bounds__(W2_THREADS, 1) mlp_tc_wgrad_kernel(const __gri
       mbar_wait(&full[stage], phase);
       const uint8_t* st = sm + stage * W2_STAGE;
       const float4* dls = reinterpret_cast<const float4*>(st + W2_DLS);
-      if ((rflags & 1) && 8 * grp < ncols_out) {
-        const uint8_t* piece = st + W2_DZ + (grp >> 3) * W2_PIECE;
+      if (rflags & 1) {
+        // 256 output columns: lane <-> 8-column group, 8 rows each; 128 columns: the two half-warps split the rows
+        const int g = ncols_out == 256 ? grp : (grp & 15);
+        const int r0 = ncols_out == 256 ? 0 : 4 * (grp >> 4), nr = ncols_out == 256 ? 8 : 4;
+        const uint8_t* piece = st + W2_DZ + (g >> 3) * W2_PIECE;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint32_t r = rset * 8 + i;
-          const uint4 v = *reinterpret_cast<const uint4*>(piece + sw128_offset(r, (uint32_t)(grp & 7) * 8));
-          float f[8];
-          unpack8(v, f);
+          if (i < nr) {
+            const uint32_t r = rset * 8 + r0 + i;
+            const uint4 v = *reinterpret_cast<const uint4*>(piece + sw128_offset(r, (uint32_t)(g & 7) * 8));
+            float f[8];
+            unpack8(v, f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc8[j] += f[j];
+            for (int j = 0; j < 8; ++j) acc8[j] += f[j];
+          }
         }
       }
       if (rflags & 2) {  // d density_w[k] += sum_s dsig[s] h8[s][k]   (X = H8, 256 columns)
@@ -665,12 +684,14 @@ __global__ void __launch_bounds__(W2_THREADS, 1) mlp_tc_wgrad_kernel(const __gri
           if (grp == 0) hb[3] += ds;
         }
       }
-      if ((rflags & 4) && grp < 16) {  // d rgb_w[c][k] += sum_s dlog[s][c] hdt[s][k]   (X = hd + appearance, 128 columns)
-        const uint8_t* piece = st + W2_X + (grp >> 3) * W2_PIECE;
+      if (rflags & 4) {  // d rgb_w[c][k] += sum_s dlog[s][c] hdt[s][k]   (X = hd + appearance, 128 columns = 16 groups;
+                         // the two half-warps take rows 0..3 / 4..7 of the row set)
+        const int g = grp & 15;
+        const uint8_t* piece = st + W2_X + (g >> 3) * W2_PIECE;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t r = rset * 8 + i;
-          const uint4 v = *reinterpret_cast<const uint4*>(piece + sw128_offset(r, (uint32_t)(grp & 7) * 8));
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t r = rset * 8 + 4 * (grp >> 4) + i;
+          const uint4 v = *reinterpret_cast<const uint4*>(piece + sw128_offset(r, (uint32_t)(g & 7) * 8));
           const float4 dl = dls[r];
           float f[8];
           unpack8(v, f);
@@ -680,28 +701,30 @@ __global__ void __launch_bounds__(W2_THREADS, 1) mlp_tc_wgrad_kernel(const __gri
             rg[1][j] = fmaf(dl.y, f[j], rg[1][j]);
             rg[2][j] = fmaf(dl.z, f[j], rg[2][j]);
           }
-          if (grp == 0) { hb[0] += dl.x; hb[1] += dl.y; hb[2] += dl.z; }
+          if (g == 0) { hb[0] += dl.x; hb[1] += dl.y; hb[2] += dl.z; }
         }
       }
       mbar_arrive_warp(&empty[stage]);
       if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
     }
     // ---- flush the CUDA-core partial sums (each of the 8 row sets holds a partial of the same columns) ----
-    if ((rflags & 1) && 8 * grp < ncols_out) {
+    if (rflags & 1) {
+      const int g = ncols_out == 256 ? grp : (grp & 15);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(wb.db + 8 * grp + j, acc8[j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(wb.db + 8 * g + j, acc8[j]);
     }
     if (rflags & 2) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) atomicAdd(plan.d_density_w + 8 * grp + j, acc8b[j]);
       if (grp == 0) atomicAdd(plan.d_density_b, hb[3]);
     }
-    if ((rflags & 4) && grp < 16) {
+    if (rflags & 4) {
+      const int g = grp & 15;
 #pragma unroll
       for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(plan.d_rgb_w + c * 128 + 8 * grp + j, rg[c][j]);
-      if (grp == 0) { atomicAdd(plan.d_rgb_b + 0, hb[0]); atomicAdd(plan.d_rgb_b + 1, hb[1]); atomicAdd(plan.d_rgb_b + 2, hb[2]); }
+        for (int j = 0; j < 8; ++j) atomicAdd(plan.d_rgb_w + c * 128 + 8 * g + j, rg[c][j]);
+      if (g == 0) { atomicAdd(plan.d_rgb_b + 0, hb[0]); atomicAdd(plan.d_rgb_b + 1, hb[1]); atomicAdd(plan.d_rgb_b + 2, hb[2]); }
     }
     mbar_wait(done, 0);
     tc_fence_after();
@@ -929,10 +952,12 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   }
   const int sms = sm_count();
   int64_t grid1 = ntiles < sms ? ntiles : sms;
+  const int dbg_all = getenv("NERFW_WGRAD_DEBUG") ? atoi(getenv("NERFW_WGRAD_DEBUG")) : 0;  // profiling switches
+  if (!(dbg_all & 16))   // bit 4: wgrad kernel only
   tcb::mlp_tc_bwd_pass1_kernel<<<(unsigned)grid1, tcb::P1_THREADS, tcb::SMEM1_BYTES, st>>>(
       reinterpret_cast<const uint8_t*>(packed), src, emb ? reinterpret_cast<const float4*>(app_off) : nullptr,
       emb ? app_vec : nullptr, reinterpret_cast<const float4*>(d_raw), total, scratch, emb ? dl_acc : nullptr,
-      reinterpret_cast<const uint32_t*>(relu_masks));
+      reinterpret_cast<const uint32_t*>(relu_masks), dbg_all);
   NERFW_LAUNCHED();
 
   // ---- pass-2 plan: one weight block and one contiguous tile range per CTA, CTAs shared out by bytes per tile ----
@@ -964,7 +989,10 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   double cost[13], csum = 0;
   for (int b = 0; b < nb; ++b) {
     const tcb::WgradBlock& wb = plan.blocks[b];
+    // units are handed out in proportion to the time of one 64-sample stage: HBM bytes (8 KB pieces; the kernel streams
+    // at ~80 % of HBM peak) or, for the rgb-head block, its CUDA-core reduction (24 FMAs per element; measured ~2x its bytes)
     cost[b] = 2.0 * wb.n_mhalves + wb.x_nblocks + 0.25;
+    if (wb.flags & 4) cost[b] *= 2.0;
     csum += cost[b];
   }
   const int max_units = sms < tcb::MAX_UNITS ? sms : tcb::MAX_UNITS;
@@ -1005,6 +1033,7 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
     }
   }
   plan.n_units = u;
+  if (!(dbg_all & 8))    // bit 3: pass 1 only
   tcb::mlp_tc_wgrad_kernel<<<(unsigned)u, tcb::W2_THREADS, tcb::SMEM2_BYTES, st>>>(plan, scratch);
   NERFW_LAUNCHED();
   if (emb) {
