@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(NerfwWeights w, uint8
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int col = cs.col0 + g * 8 + e;
+      if (cs.layer >= 1 && cs.col0 < 256) col = kperm_feature(cs.col0 >> 6, g * 8 + e);  // hidden-feature K blocks
       float v = col < K ? __ldg(W + (size_t)n * K + col) : 0.f;
       __nv_bfloat16 h = __float2bfloat16_rn(v);
       hi[e] = h;
@@ -327,9 +328,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       const bool live = s < n_total;
       // ---- trunk epilogues: acc -> bias, ReLU -> bf16 (hi[,lo]) -> next layer's A operand in TMEM ----
       float sig = 0.f;
-      // Thread <-> (row, 16-column slice cq of every 64-wide K block).  All 64 accumulator values are pulled into
-      // registers first and the accumulator is released; the four slices are then finished and published one K block at
-      // a time, so the next layer's MMAs overlap with three quarters of this epilogue.
+      // Thread <-> (row, accumulator columns 64 cq .. 64 cq + 63).  All 64 values are pulled into registers first and the
+      // accumulator is released; the four 16-column granules are then finished and published one at a time -- granule
+      // kb of the four column quarters is K block kb of the next layer (K order: kperm_feature in mlp_tc_layout.cuh) --
+      // so the next layer's MMAs overlap with three quarters of this epilogue.
       for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
@@ -340,14 +342,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         const bool want_lo = X3 && (layer != NERFW_LAYERS - 1 || dir_split);
         uint32_t r[4][16];
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) tmem_ld16(tlane + COL_ACC + kb * 64 + cq * 16, r[kb]);
+        for (int kb = 0; kb < 4; ++kb) tmem_ld16(tlane + COL_ACC + cq * 64 + kb * 16, r[kb]);
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive_warp(acc_free);
         if (tid == 0) NERFW_STAMP(15 + layer * 8);   // accumulator in registers
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
-          const uint32_t col = kb * 64 + cq * 16;
+          const uint32_t col = cq * 64 + kb * 16;         // accumulator column = output feature
+          const uint32_t apos = (kb * 64 + cq * 16) >> 1;  // operand position: granule kb of quarter cq (kperm_feature)
           const float4* b4 = reinterpret_cast<const float4*>(bias + col);
           uint32_t ph[8];
           float a[16];
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
             ph[2 * j4] = relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
             ph[2 * j4 + 1] = relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
           }
-          tmem_st8(tlane + COL_AHI + (col >> 1), ph);
+          tmem_st8(tlane + COL_AHI + apos, ph);
           if (want_lo) {  // lo = bf16(relu(a) - hi)
             uint32_t pl[8];
 #pragma unroll
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
               unpack2f(sub2(pack2f(fmaxf(a[2 * j], 0.f), fmaxf(a[2 * j + 1], 0.f)), pack2(ph[j] << 16, ph[j] & 0xffff0000u)), l0v, l1v);
               pl[j] = pack_bf16x2(l0v, l1v);
             }
-            tmem_st8(tlane + COL_ALO + (col >> 1), pl);
+            tmem_st8(tlane + COL_ALO + apos, pl);
           }
           if (masks) {  // 16 ReLU gates of this slice = one half of gate word col / 32
             uint32_t bits = 0;

@@ -49,7 +49,22 @@ constexpr uint32_t SM1_MASK_B = SM_PED_LO;  // layers 4..7
 constexpr uint32_t SM1_DSIG = SM_RGB + 4 * TM * 16;  // after the [4][128] float4 rgb partial sums
 constexpr uint32_t SM1_APPV = SM1_DSIG + TM * 4;
 constexpr uint32_t SM1_BAR = SM1_APPV + 128 * 4;
-constexpr uint32_t SM1_TMEMPTR = SM1_BAR + (2 * NSTAGES + 2) * 8;
+constexpr uint32_t SM1_TMEMPTR = SM1_BAR + (2 * NSTAGES + 2 + 5 + 2) * 8;
+// With the forward's gate masks the mask regions are free, and with a 3-stage weight ring so is the fourth ring stage:
+// together a 4 x 16 KB staging image of the 64 KB every epilogue step writes to the scratch tile.  The epilogue warps only
+// write shared memory (16-byte stores in the block image, conflict free); a dedicated warp ships each finished image with
+// four cp.async.bulk stores (TMA engine), so no st.global is issued by the epilogue warps.
+constexpr int P1_STAGES = 3;
+__device__ __forceinline__ uint32_t sm1_staging(int b) {
+  return b == 0 ? SM1_MASK_A : b == 1 ? SM1_MASK_B : SM_RING + (uint32_t)P1_STAGES * BIG_CHUNK + (uint32_t)(b - 2) * BLK;
+}
+struct Pipe3 {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == P1_STAGES) { stage = 0; phase ^= 1; }
+  }
+};
 constexpr size_t SMEM1_BYTES = SM1_TMEMPTR + 16 + 1024;
 
 __global__ void __launch_bounds__(256) pack_weights_t_kernel(NerfwWeights w, uint8_t* __restrict__ packed_t) {
@@ -70,7 +85,11 @@ __global__ void __launch_bounds__(256) pack_weights_t_kernel(NerfwWeights w, uin
   }
   __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(__ldg(W + (size_t)(ob * 64 + g * 8 + e) * ld + n));
+  for (int e = 0; e < 8; ++e) {
+    // K = the layer's output features: in operand order (kperm_feature) when dZ comes from a trunk epilogue
+    const int o = chunk < 2 ? ob * 64 + g * 8 + e : kperm_feature(ob, g * 8 + e);
+    v[e] = __float2bfloat16_rn(__ldg(W + (size_t)o * ld + n));
+  }
   *reinterpret_cast<uint4*>(packed_t + (size_t)chunk * BIG_CHUNK + sw128_offset((uint32_t)n, (uint32_t)g * 8)) =
       *reinterpret_cast<const uint4*>(v);
 }
@@ -79,7 +98,8 @@ __global__ void __launch_bounds__(256) pack_weights_t_kernel(NerfwWeights w, uin
 constexpr int P1_EPI_WARPS = 16;
 constexpr int P1_PRODUCER_WARP = 16;
 constexpr int P1_MMA_WARP = 17;
-constexpr int P1_THREADS = 576;
+constexpr int P1_STORE_WARP = 18;
+constexpr int P1_THREADS = 608;
 constexpr int P1_EPI_THREADS = P1_EPI_WARPS * 32;
 
 // own ReLU gate words (used only when the caller passes no forward masks): [layer][row][8 words], word = column / 32
@@ -148,7 +168,11 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + SM1_BAR);
   uint64_t* empty = full + NSTAGES;
   uint64_t* acc_full = empty + NSTAGES;
-  uint64_t* a_ready = acc_full + 1;
+  uint64_t* a_ready = acc_full + 1;   // per tile: encodings in place, operand columns free
+  uint64_t* acc_free = a_ready + 1;   // accumulator copied to registers
+  uint64_t* a_kb = acc_free + 1;      // [4]: K block kb of the next operand written
+  uint64_t* st_full = a_kb + 4;       // staging image of this step complete (one arrival per epilogue warp)
+  uint64_t* st_free = st_full + 1;    // staging image read out by the bulk stores
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM1_TMEMPTR);
   float* vec = reinterpret_cast<float*>(sm + SM_VEC);
   float* sig_part = reinterpret_cast<float*>(sm + SM_SIG);
@@ -160,6 +184,10 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
     mbar_init(a_ready, P1_EPI_WARPS);   // one arrival per epilogue warp
+    mbar_init(acc_free, P1_EPI_WARPS);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_kb[i], P1_EPI_WARPS);
+    mbar_init(st_full, P1_EPI_WARPS);
+    mbar_init(st_free, 1);
     fence_mbar_init();
   }
   if (warp == P1_MMA_WARP) tmem_alloc<512>(tmem_ptr);
@@ -179,7 +207,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
 
   if (warp == P1_PRODUCER_WARP) {
     if (lane == 0) {
-      Pipe p;
+      Pipe3 p;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int i = 0; i < N_CHUNKS; ++i) {  // forward stream (hi copies only)
           const uint32_t sz = i < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
@@ -196,9 +224,35 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         }
       }
     }
+  } else if (warp == P1_STORE_WARP) {
+    // ===================== scratch-tile stores: one bulk copy per 16 KB block of every finished staging image =========
+    if (lane == 0 && fwd_masks && !(debug & 4)) {
+      uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint8_t* tsc = scratch + (size_t)tile * TILE_BYTES;
+        for (int step = 0; step < 17; ++step) {   // 8 forward layers, direction layer, 8 dgrad layers (7 .. 0)
+          mbar_wait(st_full, ph);
+          ph ^= 1;
+          if (step == 8) {
+            bulk_s2g(tsc + (size_t)ZB_DIR * BLK, sm + sm1_staging(0), BLK);
+            bulk_s2g(tsc + (size_t)(ZB_DIR + 1) * BLK, sm + sm1_staging(1), BLK);
+            bulk_s2g(tsc + (size_t)XB_HDT * BLK, sm + sm1_staging(2), 2 * BLK);
+          } else {
+            const int b0 = step < 8 ? XB_H(step + 1) : ZB(16 - step);
+            bulk_s2g(tsc + (size_t)b0 * BLK, sm + sm1_staging(0), BLK);
+            bulk_s2g(tsc + (size_t)(b0 + 1) * BLK, sm + sm1_staging(1), BLK);
+            bulk_s2g(tsc + (size_t)(b0 + 2) * BLK, sm + sm1_staging(2), 2 * BLK);
+          }
+          bulk_commit();
+          bulk_wait_read_all();
+          mbar_arrive(st_free);
+        }
+      }
+      bulk_wait_all();
+    }
   } else if (warp == P1_MMA_WARP) {
     if (lane == 0) {
-      Pipe p;
+      Pipe3 p;
       uint32_t ar_phase = 0;
       const uint32_t idesc256 = idesc_bf16(128, 256), idesc128 = idesc_bf16(128, 128);
       const uint32_t ring = smem_u32(sm + SM_RING);
@@ -217,34 +271,45 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
       };
       const uint64_t pex = smem_desc_sw128(smem_u32(sm + SM_PEX_HI));
       const uint64_t ped = smem_desc_sw128(smem_u32(sm + SM_PED_HI));
-      auto wait_a = [&]() {
-        mbar_wait(a_ready, ar_phase);
-        ar_phase ^= 1;
+      // Handshakes per MMA step: acc_free (the previous accumulator sits in registers), then one barrier per 64-wide K
+      // block of the operand -- the epilogue publishes its four 16-column granules one at a time (K order: kperm_feature),
+      // so the MMAs of a step start while three quarters of the previous epilogue are still running.
+      uint32_t ph_free = 0, ph_kb[4] = {0, 0, 0, 0};
+      auto wait_bar = [&](uint64_t* bar, uint32_t& phase) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
         tc_fence_after();
       };
+      auto from_tmem = [&](int nkb, uint32_t idesc) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          wait_bar(&a_kb[kb], ph_kb[kb]);
+          kblock(true, tmem + COL_AHI + 32 * kb, idesc, 4, kb == 0);
+        }
+      };
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        wait_bar(a_ready, ar_phase);
         // ---- forward recompute ----
         for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
-          wait_a();
+          wait_bar(acc_free, ph_free);
           if (layer == 0) {
             kblock(false, pex, idesc256, 4, true);
           } else {
-            for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, idesc256, 4, kb == 0);
+            from_tmem(4, idesc256);
             if (layer == NERFW_SKIP) kblock(false, pex, idesc256, 4, false);
           }
           mma_commit(acc_full);
         }
-        wait_a();
-        for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, idesc128, 4, kb == 0);
+        wait_bar(acc_free, ph_free);
+        from_tmem(4, idesc128);
         kblock(false, ped, idesc128, 2, false);
         mma_commit(acc_full);
         // ---- dgrad chain: dH8 = dZdir W_dir[:, :256], then dH_l = dZ_l W_l[:, :256] for l = 7..1 ----
-        wait_a();
-        for (int kb = 0; kb < 2; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, idesc256, 4, kb == 0);
+        wait_bar(acc_free, ph_free);
+        from_tmem(2, idesc256);
         mma_commit(acc_full);
         for (int l = NERFW_LAYERS - 1; l >= 1; --l) {
-          wait_a();
-          for (int kb = 0; kb < 4; ++kb) kblock(true, tmem + COL_AHI + 32 * kb, idesc256, 4, kb == 0);
+          wait_bar(acc_free, ph_free);
+          from_tmem(4, idesc256);
           mma_commit(acc_full);
         }
       }
@@ -258,11 +323,20 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
     uint8_t* pex = sm + SM_PEX_HI;
     uint8_t* ped = sm + SM_PED_HI;
     // with the forward's gates the mask region of shared memory is free: 16 x 2 KB staging buffers for coalesced stores
-    uint8_t* stage = fwd_masks ? sm + (warp < 8 ? SM1_MASK_A : SM1_MASK_B) + (warp & 7) * 2048 : nullptr;
-    auto put = [&](uint8_t* tile_base, int block0, uint32_t col, const uint32_t (&p)[16]) {
+    // with the forward's gates: 32-column pieces go to block `sblock` of the staging image (shipped by the store warp);
+    // without them the mask regions are in use and the pieces are stored directly (slow path, API completeness only)
+    const bool staged = fwd_masks != nullptr;
+    uint32_t st_phase = 0;
+    auto put = [&](uint8_t* tile_base, int block0, int sblock, uint32_t col, const uint32_t (&p)[16]) {
       if (debug & 4) return;   // profiling only (NERFW_WGRAD_DEBUG bit 2): no scratch stores
-      if (stage) store_row32_staged(stage, tile_base, block0, quad * 32, lane, col, p);
+      if (staged) store_row32(sm + sm1_staging(sblock) - (size_t)(col >> 6) * BLK, 0, row, col, p);
       else store_row32(tile_base, block0, row, col, p);
+    };
+    auto staging_acquire = [&]() {   // the previous image has been read out
+      if (staged && !(debug & 4)) { mbar_wait(st_free, st_phase ^ 1); st_phase ^= 1; }
+    };
+    auto staging_release = [&]() {
+      if (staged && !(debug & 4)) { fence_proxy_async_smem(); mbar_arrive_warp(st_full); }
     };
     // ---- encodings (as in the bf16 forward kernel) of tile t into shared memory and, as wgrad operands of layer 0, of the
     // skip part of layer 4 and of the direction layer, into its scratch tile.  Off the critical path: the encodings of
@@ -296,6 +370,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         *reinterpret_cast<uint4*>(dst + (size_t)XB_ENCD * BLK + o) = *reinterpret_cast<const uint4*>(ped + o);
       }
     };
+    mbar_arrive_warp(acc_free);   // the accumulator starts out free
     if ((int64_t)blockIdx.x < ntiles) {
       encode_tile(blockIdx.x);
       mbar_arrive_warp(a_ready);
@@ -313,55 +388,50 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         tc_fence_after();
         const float* bias = vec + V_PTSB + layer * 256;
         const bool plain = fwd_masks != nullptr && layer != NERFW_LAYERS - 1;  // warp-uniform
-        uint32_t ph2[2][16];   // both 32-column halves: handed to the MMA thread first, stored to the scratch tile after
+        // thread <-> accumulator columns 64 cq .. 64 cq + 63: into registers, accumulator released, then granule by granule
+        uint32_t r[4][16];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint32_t col = cq * 64 + q * 32;
-          uint32_t (&ph)[16] = ph2[q];
-          uint32_t r[32];
-          tmem_ld32(tlane + COL_ACC + col, r);
-          tmem_wait_ld();
+        for (int j = 0; j < 4; ++j) tmem_ld16(tlane + COL_ACC + cq * 64 + j * 16, r[j]);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_warp(acc_free);
+        uint32_t ph2[2][16];   // the same values as two 32-column pieces for the scratch tile
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t col = cq * 64 + j * 16;
           const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-          if (plain) {
+          uint32_t* ph = &ph2[j >> 1][(j & 1) * 8];
+          float a[16];
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4];
-              float a0, a1, a2, a3;
-              unpack2f(add2(pack2(r[4 * j4], r[4 * j4 + 1]), pack2f(bb.x, bb.y)), a0, a1);
-              unpack2f(add2(pack2(r[4 * j4 + 2], r[4 * j4 + 3]), pack2f(bb.z, bb.w)), a2, a3);
-              ph[2 * j4] = relu_pack_bf16x2(a0, a1);
-              ph[2 * j4 + 1] = relu_pack_bf16x2(a2, a3);
-            }
-          } else {
-            float v[32];
-            uint32_t bits = 0;
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4];
-              v[4 * j4] = fmaxf(__uint_as_float(r[4 * j4]) + bb.x, 0.f);
-              v[4 * j4 + 1] = fmaxf(__uint_as_float(r[4 * j4 + 1]) + bb.y, 0.f);
-              v[4 * j4 + 2] = fmaxf(__uint_as_float(r[4 * j4 + 2]) + bb.z, 0.f);
-              v[4 * j4 + 3] = fmaxf(__uint_as_float(r[4 * j4 + 3]) + bb.w, 0.f);
-            }
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = b4[j4];
+            unpack2f(add2(pack2(r[j][4 * j4], r[j][4 * j4 + 1]), pack2f(bb.x, bb.y)), a[4 * j4], a[4 * j4 + 1]);
+            unpack2f(add2(pack2(r[j][4 * j4 + 2], r[j][4 * j4 + 3]), pack2f(bb.z, bb.w)), a[4 * j4 + 2], a[4 * j4 + 3]);
+            ph[2 * j4] = relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
+            ph[2 * j4 + 1] = relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
+          }
+          if (!plain) {
             if (!fwd_masks) {
+              uint32_t bits = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-              mask_words(sm, layer, row)[col >> 5] = bits;
+              for (int e = 0; e < 16; ++e) bits |= (a[e] > 0.f ? 1u : 0u) << e;
+              reinterpret_cast<unsigned short*>(mask_words(sm, layer, row))[col >> 4] = (unsigned short)bits;
             }
             if (layer == NERFW_LAYERS - 1) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) sig = fmaf(v[j], vec[V_DENW + col + j], sig);
+              for (int e = 0; e < 16; ++e) sig = fmaf(fmaxf(a[e], 0.f), vec[V_DENW + col + e], sig);
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           }
-          tmem_st16(tlane + COL_AHI + (col >> 1), ph);
+          const uint32_t p8[8] = {ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]};
+          tmem_st8(tlane + COL_AHI + ((j * 64 + cq * 16) >> 1), p8);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive_warp(&a_kb[j]);
         }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive_warp(a_ready);
+        staging_acquire();
 #pragma unroll
-        for (int q = 0; q < 2; ++q) put(tsc, XB_H(layer + 1), cq * 64 + q * 32, ph2[q]);
+        for (int q = 0; q < 2; ++q) put(tsc, XB_H(layer + 1), (int)cq, cq * 64 + q * 32, ph2[q]);
+        staging_release();
       }
       sig_part[cq * TM + row] = sig;
 
@@ -377,6 +447,8 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         uint32_t r[32];
         tmem_ld32(tlane + COL_ACC + dcol, r);
         tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_warp(acc_free);
         uint32_t bits = 0;
         float hv[32];
 #pragma unroll
@@ -435,12 +507,15 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
           const float g1 = dlog[0] * vec[V_RGBW + c0 + 1] + dlog[1] * vec[V_RGBW + 128 + c0 + 1] + dlog[2] * vec[V_RGBW + 256 + c0 + 1];
           ph[j] = gate_pack(g0, g1, hmask, j);
         }
-        tmem_st16(tlane + COL_AHI + (dcol >> 1), ph);
+        tmem_st16(tlane + COL_AHI + (dcol >> 1), ph);   // K = direction-layer feature, natural order (2 K blocks)
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive_warp(a_ready);
-        put(tsc, ZB_DIR, dcol, ph);
-        put(tsc, XB_HDT, dcol, ph_hdt);
+        mbar_arrive_warp(&a_kb[0]);
+        mbar_arrive_warp(&a_kb[1]);
+        staging_acquire();
+        put(tsc, ZB_DIR, (int)(dcol >> 6), dcol, ph);
+        put(tsc, XB_HDT, 2 + (int)(dcol >> 6), dcol, ph_hdt);
+        staging_release();
       }
       named_bar_sync(1, P1_EPI_THREADS);  // dsig_s visible to every column quarter
 
@@ -456,42 +531,47 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         tc_fence_after();
         const float ds = dsig_s[row];
         const uint64_t ds2 = pack2f(ds, ds);
+        uint32_t r[4][16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmem_ld16(tlane + COL_ACC + cq * 64 + j * 16, r[j]);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_warp(acc_free);
         uint32_t ph2[2][16];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint32_t col = cq * 64 + q * 32;
-          uint32_t (&ph)[16] = ph2[q];
-          uint32_t r[32];
-          tmem_ld32(tlane + COL_ACC + col, r);
-          tmem_wait_ld();
-          const uint32_t bits = fwd_masks ? gate[q] : mask_words(sm, l, row)[col >> 5];
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t col = cq * 64 + j * 16;
+          const uint32_t word = fwd_masks ? gate[j >> 1] : mask_words(sm, l, row)[col >> 5];
+          const uint32_t bits = word >> ((j & 1) * 16);
+          uint32_t* ph = &ph2[j >> 1][(j & 1) * 8];
           if (l == NERFW_LAYERS - 1) {  // + density head: d sigma_pre * w_sigma
             const float2* w2 = reinterpret_cast<const float2*>(vec + V_DENW + col);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 ww = w2[j];
+            for (int e = 0; e < 8; ++e) {
+              const float2 ww = w2[e];
               float g0, g1;
-              unpack2f(fma2(ds2, pack2f(ww.x, ww.y), pack2(r[2 * j], r[2 * j + 1])), g0, g1);
-              ph[j] = gate_pack(g0, g1, bits, j);
+              unpack2f(fma2(ds2, pack2f(ww.x, ww.y), pack2(r[j][2 * e], r[j][2 * e + 1])), g0, g1);
+              ph[e] = gate_pack(g0, g1, bits, e);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) ph[j] = gate_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), bits, j);
+            for (int e = 0; e < 8; ++e) ph[e] = gate_pack(__uint_as_float(r[j][2 * e]), __uint_as_float(r[j][2 * e + 1]), bits, e);
           }
-          if (l > 0) tmem_st16(tlane + COL_AHI + (col >> 1), ph);
+          if (l > 0) {
+            const uint32_t p8[8] = {ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]};
+            tmem_st8(tlane + COL_AHI + ((j * 64 + cq * 16) >> 1), p8);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive_warp(&a_kb[j]);
+          }
         }
-        if (l > 0) {
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive_warp(a_ready);
-        } else {
-          tc_fence_before();
-          // accumulator and operand columns are free and the next tile's encodings are in place (written below, during
-          // the dgrad phase): its layer 0 may start while this tile's last dZ block is still being stored
-          if (tile + gridDim.x < ntiles) mbar_arrive_warp(a_ready);
-        }
+        // accumulator and operand columns are free and the next tile's encodings are in place (written during the dgrad
+        // phase): its layer 0 may start while this tile's last dZ block is still being stored
+        if (l == 0 && tile + gridDim.x < ntiles) mbar_arrive_warp(a_ready);
+        staging_acquire();
 #pragma unroll
-        for (int q = 0; q < 2; ++q) put(tsc, ZB(l), cq * 64 + q * 32, ph2[q]);
+        for (int q = 0; q < 2; ++q) put(tsc, ZB(l), (int)cq, cq * 64 + q * 32, ph2[q]);
+        staging_release();
         if (l == NERFW_LAYERS - 2 && tile + gridDim.x < ntiles) encode_tile(tile + gridDim.x);
       }
     }

@@ -65,6 +65,12 @@ __host__ __device__ inline ChunkSrc chunk_source(int i) {
   if (i < 30) return {5 + (i - 18) / 4, ((i - 18) % 4) * 64};
   return {8, (i - 30) * 64};              // i == 34: columns 256.. = enc_d part
 }
+// K order inside the 256 hidden features of an operand produced by a trunk epilogue.  An epilogue thread owns 64
+// CONTIGUOUS accumulator columns (column quarter cq: columns 64 cq .. 64 cq + 63, so its activation / gradient rows are
+// stored to the scratch tiles in 64-byte pieces) but hands them to the MMA thread in four 16-column granules j; granule j
+// of all four quarters forms K block j of the next MMA.  Position p = 16 cq + i of K block j therefore holds feature
+// 64 cq + 16 j + i, and every weight image consumed with such an operand is packed in the same order.
+__host__ __device__ inline int kperm_feature(int kblock, int pos) { return 64 * (pos >> 4) + 16 * kblock + (pos & 15); }
 __host__ __device__ inline size_t chunk_offset(int i) {  // byte offset of the hi copy; lo follows at +size
   return i < N_BIG ? 2ull * i * BIG_CHUNK : 2ull * N_BIG * BIG_CHUNK + 2ull * (i - N_BIG) * SMALL_CHUNK;
 }
