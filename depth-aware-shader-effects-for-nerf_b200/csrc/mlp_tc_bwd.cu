@@ -155,13 +155,17 @@ __device__ __forceinline__ void store_row32_staged(uint8_t* stage, uint8_t* tile
 }
 
 // ====================================================================================================================
+// profiling: clock64 stamps of CTA 0, third tile (slot = 16 + 8 * step + event); only when a timeline buffer is passed
+#define P1_STAMP(slot) do { if (timeline && blockIdx.x == 0 && tile == (int64_t)(2 * gridDim.x)) timeline[slot] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const uint8_t* __restrict__ packed, SampleSource src,
                                                                        const float4* __restrict__ app_off,
                                                                        const float* __restrict__ app_vec,
                                                                        const float4* __restrict__ d_raw, int64_t n_total,
                                                                        uint8_t* __restrict__ scratch,
                                                                        float* __restrict__ dl_acc,
-                                                                       const uint32_t* __restrict__ fwd_masks, int debug) {
+                                                                       const uint32_t* __restrict__ fwd_masks, int debug,
+                                                                       long long* __restrict__ timeline) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -280,17 +284,24 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         phase ^= 1;
         tc_fence_after();
       };
+      int64_t tile = 0;
+      int step = 0;
       auto from_tmem = [&](int nkb, uint32_t idesc) {
         for (int kb = 0; kb < nkb; ++kb) {
           wait_bar(&a_kb[kb], ph_kb[kb]);
+          if (kb == 0) P1_STAMP(16 + 8 * step + 1);
+          if (kb == nkb - 1) P1_STAMP(16 + 8 * step + 2);
           kblock(true, tmem + COL_AHI + 32 * kb, idesc, 4, kb == 0);
         }
       };
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         wait_bar(a_ready, ar_phase);
+        P1_STAMP(0);
         // ---- forward recompute ----
         for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
+          step = layer;
           wait_bar(acc_free, ph_free);
+          P1_STAMP(16 + 8 * step + 0);
           if (layer == 0) {
             kblock(false, pex, idesc256, 4, true);
           } else {
@@ -298,19 +309,29 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
             if (layer == NERFW_SKIP) kblock(false, pex, idesc256, 4, false);
           }
           mma_commit(acc_full);
+          P1_STAMP(16 + 8 * step + 3);
         }
+        step = 8;
         wait_bar(acc_free, ph_free);
+        P1_STAMP(16 + 8 * step + 0);
         from_tmem(4, idesc128);
         kblock(false, ped, idesc128, 2, false);
         mma_commit(acc_full);
+        P1_STAMP(16 + 8 * step + 3);
         // ---- dgrad chain: dH8 = dZdir W_dir[:, :256], then dH_l = dZ_l W_l[:, :256] for l = 7..1 ----
+        step = 9;
         wait_bar(acc_free, ph_free);
+        P1_STAMP(16 + 8 * step + 0);
         from_tmem(2, idesc256);
         mma_commit(acc_full);
+        P1_STAMP(16 + 8 * step + 3);
         for (int l = NERFW_LAYERS - 1; l >= 1; --l) {
+          step = 10 + (NERFW_LAYERS - 1 - l);
           wait_bar(acc_free, ph_free);
+          P1_STAMP(16 + 8 * step + 0);
           from_tmem(4, idesc256);
           mma_commit(acc_full);
+          P1_STAMP(16 + 8 * step + 3);
         }
       }
     }
@@ -388,6 +409,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         tc_fence_after();
         const float* bias = vec + V_PTSB + layer * 256;
         const bool plain = fwd_masks != nullptr && layer != NERFW_LAYERS - 1;  // warp-uniform
+        if (tid == 0) P1_STAMP(16 + 8 * (layer + 1) + 4);   // accumulator of step `layer` complete (slot of the next step)
         // thread <-> accumulator columns 64 cq .. 64 cq + 63: into registers, accumulator released, then granule by granule
         uint32_t r[4][16];
 #pragma unroll
@@ -427,11 +449,14 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive_warp(&a_kb[j]);
+          if (tid == 0 && j == 0) P1_STAMP(16 + 8 * (layer + 1) + 5);
+          if (tid == 0 && j == 3) P1_STAMP(16 + 8 * (layer + 1) + 6);
         }
         staging_acquire();
 #pragma unroll
         for (int q = 0; q < 2; ++q) put(tsc, XB_H(layer + 1), (int)cq, cq * 64 + q * 32, ph2[q]);
         staging_release();
+        if (tid == 0) P1_STAMP(16 + 8 * (layer + 1) + 7);
       }
       sig_part[cq * TM + row] = sig;
 
@@ -512,6 +537,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         tc_fence_before();
         mbar_arrive_warp(&a_kb[0]);
         mbar_arrive_warp(&a_kb[1]);
+        if (tid == 0) P1_STAMP(16 + 8 * 9 + 5);
         staging_acquire();
         put(tsc, ZB_DIR, (int)(dcol >> 6), dcol, ph);
         put(tsc, XB_HDT, 2 + (int)(dcol >> 6), dcol, ph_hdt);
@@ -529,6 +555,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        if (tid == 0) P1_STAMP(16 + 8 * (10 + (NERFW_LAYERS - 1 - l)) + 4);
         const float ds = dsig_s[row];
         const uint64_t ds2 = pack2f(ds, ds);
         uint32_t r[4][16];
@@ -563,6 +590,8 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive_warp(&a_kb[j]);
+            if (tid == 0 && j == 0) P1_STAMP(16 + 8 * (10 + (NERFW_LAYERS - 1 - l)) + 5);
+            if (tid == 0 && j == 3) P1_STAMP(16 + 8 * (10 + (NERFW_LAYERS - 1 - l)) + 6);
           }
         }
         // accumulator and operand columns are free and the next tile's encodings are in place (written during the dgrad
@@ -572,6 +601,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
 #pragma unroll
         for (int q = 0; q < 2; ++q) put(tsc, ZB(l), (int)cq, cq * 64 + q * 32, ph2[q]);
         staging_release();
+        if (tid == 0) P1_STAMP(16 + 8 * (10 + (NERFW_LAYERS - 1 - l)) + 7);
         if (l == NERFW_LAYERS - 2 && tile + gridDim.x < ntiles) encode_tile(tile + gridDim.x);
       }
     }
@@ -1037,7 +1067,8 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   tcb::mlp_tc_bwd_pass1_kernel<<<(unsigned)grid1, tcb::P1_THREADS, tcb::SMEM1_BYTES, st>>>(
       reinterpret_cast<const uint8_t*>(packed), src, emb ? reinterpret_cast<const float4*>(app_off) : nullptr,
       emb ? app_vec : nullptr, reinterpret_cast<const float4*>(d_raw), total, scratch, emb ? dl_acc : nullptr,
-      reinterpret_cast<const uint32_t*>(relu_masks), dbg_all);
+      reinterpret_cast<const uint32_t*>(relu_masks), dbg_all,
+      getenv("NERFW_BWD_TIMELINE") ? reinterpret_cast<long long*>(strtoull(getenv("NERFW_BWD_TIMELINE"), nullptr, 10)) : nullptr);
   NERFW_LAUNCHED();
 
   // ---- pass-2 plan: one weight block and one contiguous tile range per CTA, CTAs shared out by bytes per tile ----
