@@ -172,6 +172,82 @@ __global__ void __launch_bounds__(CP_WARPS * 32) composite_bwd_kernel(
   }
 }
 
+// Register-resident variant for N <= 32 NC (NC <= 8): the ray is read ONCE -- every lane keeps its NC float4 records,
+// depths and per-sample factors in registers between the forward sweep and the reverse sweep, all loads of a ray are in
+// flight together, and the depth of the next chunk's first sample comes from a shuffle instead of a second load.  Same
+// arithmetic in the same order as the generic kernel above, so the results are bit-identical.
+template <int NC>
+__global__ void __launch_bounds__(CP_WARPS * 32) composite_bwd_reg_kernel(
+    const float4* __restrict__ raw, const float* __restrict__ z, int64_t B, int N, const float* __restrict__ d_rgb_map,
+    const float* __restrict__ d_depth, const float* __restrict__ d_acc, const float* __restrict__ d_weights,
+    float4* __restrict__ d_raw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * CP_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * CP_WARPS;
+  for (int64_t ray = warp0; ray < B; ray += nwarps) {
+    const float4* rr = raw + ray * N;
+    const float* zr = z + ray * N;
+    float4 s[NC];
+    float zv[NC], dw[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int i = c * 32 + lane;
+      const bool on = i < N;
+      s[c] = on ? ld_stream4(rr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      zv[c] = on ? __ldg(zr + i) : 0.f;
+      dw[c] = (d_weights && on) ? __ldg(d_weights + ray * N + i) : 0.f;
+    }
+    const float gr = __ldg(d_rgb_map + ray * 3 + 0), gg = __ldg(d_rgb_map + ray * 3 + 1), gb = __ldg(d_rgb_map + ray * 3 + 2);
+    const float gd_raw = d_depth ? __ldg(d_depth + ray) : 0.f;
+    const float ga = d_acc ? __ldg(d_acc + ray) : 0.f;
+    float delta[NC], e[NC], T[NC];
+    float carry = 1.0f, sw = 0.f, swz = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int i = c * 32 + lane;
+      const bool on = i < N;
+      float zn = __shfl_down_sync(0xffffffffu, zv[c], 1);
+      const float znext = __shfl_sync(0xffffffffu, zv[c + 1 < NC ? c + 1 : c], 0);  // first depth of the next chunk
+      if (lane == 31) zn = znext;
+      delta[c] = (i + 1 < N) ? (zn - zv[c]) : LAST_DELTA;
+      e[c] = on ? expf(-s[c].w * delta[c]) : 1.0f;
+      const float alpha = on ? (1.0f - e[c]) : 0.f;
+      const float t = on ? ((1.0f - alpha) + T_EPS) : 1.0f;
+      const float incl = warp_scan_mul(t, lane);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      T[c] = carry * excl;
+      const float w = alpha * T[c];
+      carry *= __shfl_sync(0xffffffffu, incl, 31);
+      sw += w; swz += w * zv[c];
+    }
+    sw = warp_sum(sw); swz = warp_sum(swz);
+    const float wden = sw + T_EPS;
+    const float dep = swz / wden;
+    const float gd = d_depth ? gd_raw / wden : 0.f;
+    float suffix = 0.f;  // sum of g_k w_k over later chunks
+#pragma unroll
+    for (int c = NC - 1; c >= 0; --c) {
+      const int i = c * 32 + lane;
+      const bool on = i < N;
+      const float alpha = on ? (1.0f - e[c]) : 0.f;
+      const float t = on ? ((1.0f - alpha) + T_EPS) : 1.0f;
+      const float w = alpha * T[c];
+      float g = gr * s[c].x + gg * s[c].y + gb * s[c].z + gd * (zv[c] - dep) + ga;
+      if (d_weights && on) g += dw[c];
+      const float gw = on ? g * w : 0.f;
+      const float rs = warp_rscan_add(gw, lane);
+      const float after = (rs - gw) + suffix;
+      suffix += __shfl_sync(0xffffffffu, rs, 0);
+      if (on) {
+        const float dalpha = g * T[c] - after / t;
+        const float dsigma = dalpha * delta[c] * e[c];
+        d_raw[ray * N + i] = make_float4(w * gr, w * gg, w * gb, dsigma);
+      }
+    }
+  }
+}
+
 }  // namespace nerfw
 
 using namespace nerfw;
@@ -202,9 +278,17 @@ extern "C" int nerfw_composite_bwd(const float* raw, const float* z, int64_t n_r
   if (n_rays == 0) return NERFW_OK;
   NERFW_REQUIRE(raw && z && d_rgb_map && d_raw, "nerfw_composite_bwd: null pointer");
   NERFW_REQUIRE(aligned16(raw) && aligned16(d_raw), "nerfw_composite_bwd: raw/d_raw must be 16-byte aligned");
-  composite_bwd_kernel<<<comp_grid(n_rays), CP_WARPS * 32, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(raw), z, n_rays, n_samples, d_rgb_map, d_depth, d_acc, d_weights,
-      reinterpret_cast<float4*>(d_raw));
+  const int nchunks = (n_samples + 31) / 32;
+  auto launch = [&](auto kernel) {
+    kernel<<<comp_grid(n_rays), CP_WARPS * 32, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(raw), z, n_rays, n_samples, d_rgb_map, d_depth, d_acc, d_weights,
+        reinterpret_cast<float4*>(d_raw));
+  };
+  if (nchunks <= 2) launch(composite_bwd_reg_kernel<2>);        // 64 coarse samples
+  else if (nchunks <= 4) launch(composite_bwd_reg_kernel<4>);
+  else if (nchunks <= 6) launch(composite_bwd_reg_kernel<6>);   // 64 + 128
+  else if (nchunks <= 8) launch(composite_bwd_reg_kernel<8>);
+  else launch(composite_bwd_kernel);
   NERFW_LAUNCHED();
   return NERFW_OK;
 }
