@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- render throughput of the NeRF-W ray-marching hot path (BASELINE.json metric: render Mrays/s, 64+128).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mlp-mode bf16x3|bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mlp-mode mixed|bf16x3|fp16|bf16|fp32]
 
 A step = one synthetic 800x800 view (640 000 rays) rendered coarse(64) + fine(64+128) with random-init NeRF-W weights
 (BASELINE.json configs[1]).  `value` is timed with the rays already in HBM; `e2e` goes through the public API with the
@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mlp-mode", default=os.environ.get("NERFW_MLP_MODE", "bf16x3"), choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--mlp-mode", default=os.environ.get("NERFW_MLP_MODE", "mixed"), choices=["mixed", "bf16x3", "fp16", "bf16", "fp32"],
+                    help="mixed (default): bf16x3 coarse pass + fp16 fine pass, the cheapest arithmetic inside the fp32 parity bars")
     ap.add_argument("--cpu-rays", type=int, default=int(os.environ.get("NERFW_CPU_SAMPLE_RAYS", "24000")),
                     help="rays in the bounded CPU sample (cpu_baseline / --impl reference step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -311,36 +312,48 @@ def run_ours(args):
         packed = model.packed_weights(names, tensors)
         emb2 = emb_d.unsqueeze(0).contiguous()
         roof = {}
-        for m in sorted({mode, "bf16"}):
+        z_coarse = out[2]["z_vals_coarse"].contiguous()
+        fine_mode = "fp16" if mode == "mixed" else mode          # kernel arithmetic of the fine pass (the dominant launch)
+        # (label, kernel mode, depths): the fine-pass launch of the headline mode, bf16 on the same shape, and -- for the
+        # mixed mode -- the bf16x3 coarse-pass launch
+        roof_runs = [(mode, fine_mode, z_fine), ("bf16", "bf16", z_fine)]
+        if mode == "mixed":
+            roof_runs.append(("coarse_bf16x3", "bf16x3", z_coarse))
+        for label, m, zz in roof_runs:
+            if label in roof:
+                continue
             mid = nerfw.models.resolve_mode(m)
             for _ in range(2):
-                raw = ops.mlp_fwd(pd, packed, o_dev, dn, z_fine, emb2, mid)
+                raw_m = ops.mlp_fwd(pd, packed, o_dev, dn, zz, emb2, mid)
             k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = max(2, args.steps)
             k0.record()
             for _ in range(reps):
-                raw = ops.mlp_fwd(pd, packed, o_dev, dn, z_fine, emb2, mid)
+                raw_m = ops.mlp_fwd(pd, packed, o_dev, dn, zz, emb2, mid)
             k1.record()
             torch.cuda.synchronize()
+            if zz is z_fine:
+                raw = raw_m
             kms = k0.elapsed_time(k1) / reps
-            flops = FLOP_PER_SAMPLE * float(z_fine.numel())
+            flops = FLOP_PER_SAMPLE * float(zz.numel())
             ach = flops / (kms * 1e-3) / 1e12
-            roof[m] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                       "frac": ach / peaks["bf16_tflops_sustained"],
-                       # DRAM bytes per launch: 18.9 B/sample measured by ncu --set full on a 160k-ray crop
-                       # (profiles/r01_ncu_full_*.md: 141 MB read + 439 MB written for 30.7 M samples) x samples here
-                       "traffic": 18.9 * float(z_fine.numel()),
-                       "kernel": "mlp_tc_fwd_kernel" if m != "fp32" else "mlp_ffma_fwd_kernel",
-                       "kernel_ms": kms, "samples_per_launch": int(z_fine.numel()),
-                       "peak_source": f"bf16 dense sustained, {peaks['source']}",
-                       # tensor-pipe FLOPs actually issued: bf16x3 runs the trunk as 3 MMAs per product (the direction layer
-                       # as one), heads stay on CUDA cores: 3 018 496 issued vs 1 063 936 algorithmic FLOP per sample
-                       "issued": (ach * 3018496.0 / FLOP_PER_SAMPLE) if m == "bf16x3" else ach * 1054464.0 / FLOP_PER_SAMPLE,
-                       "issued_frac": ((ach * 3018496.0 / FLOP_PER_SAMPLE) if m == "bf16x3" else ach * 1054464.0 / FLOP_PER_SAMPLE)
-                       / peaks["bf16_tflops_sustained"],
-                       "note": ("bf16x3 (fp32-parity split) issues 3 bf16 MMAs per trunk product, so the algorithmic frac is "
-                                "bounded by ~0.35; issued_frac is the tensor-pipe rate against the same peak"
-                                if m == "bf16x3" else "")}
+            # tensor-pipe FLOPs actually issued: bf16x3 runs the trunk as 3 MMAs per product (the direction layer as one),
+            # heads stay on CUDA cores: 3 018 496 issued vs 1 063 936 algorithmic FLOP per sample; single-pass modes 1 054 464
+            issued = ach * (3018496.0 if m == "bf16x3" else 1054464.0) / FLOP_PER_SAMPLE
+            roof[label] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                           "frac": ach / peaks["bf16_tflops_sustained"],
+                           # DRAM bytes per launch: 18.9 B/sample measured by ncu --set full on a 160k-ray crop
+                           # (profiles/r01_ncu_full_*.md: 141 MB read + 439 MB written for 30.7 M samples) x samples here
+                           "traffic": 18.9 * float(zz.numel()),
+                           "kernel": ("mlp_tc_fwd_kernel<%s>" % {"bf16x3": "X3", "fp16": "F16", "bf16": "BF16"}[m]) if m != "fp32" else "mlp_ffma_fwd_kernel",
+                           "kernel_mode": m, "kernel_ms": kms, "samples_per_launch": int(zz.numel()),
+                           "peak_source": f"bf16 dense sustained (fp16 and bf16 share the kind::f16 tensor-pipe rate), {peaks['source']}",
+                           "issued": issued, "issued_frac": issued / peaks["bf16_tflops_sustained"],
+                           "note": ("bf16x3 (fp32-parity split) issues 3 bf16 MMAs per trunk product, so the algorithmic frac is "
+                                    "bounded by ~0.35; issued_frac is the tensor-pipe rate against the same peak"
+                                    if m == "bf16x3" else
+                                    "fine pass of the mixed mode: single fp16 MMA per product; the coarse pass (1/4 of the samples) "
+                                    "runs in bf16x3, see roofline_other.mlp_coarse_bf16x3" if label == "mixed" else "")}
         # HBM-bound kernels on the same frame
         comp0, comp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ops.composite_fwd(raw, z_fine)
@@ -381,7 +394,7 @@ def run_ours(args):
 
     # ---- secondary numbers: the other tensor-core mode, and the training step (BASELINE.json configs[2]) ------------
     other_modes = {}
-    for m in ("bf16", "bf16x3"):
+    for m in ("bf16", "bf16x3", "mixed"):
         if m == mode:
             continue
         with torch.no_grad():
@@ -414,6 +427,8 @@ def run_ours(args):
                                                  "ms_per_step": chunk_ms, "mlp_mode": mode,
                                                  "calls_per_frame": (n_rays + 4095) // 4096}
     train = bench_train_step(nerfw, sd, dev, world, mode)
+    if mode != "bf16x3":
+        train["bf16x3_forward_ms_per_step"] = bench_train_step(nerfw, sd, dev, world, "bf16x3")["ms_per_step"]
     if mode != "bf16":
         train["bf16_forward_ms_per_step"] = bench_train_step(nerfw, sd, dev, world, "bf16")["ms_per_step"]
 
@@ -442,7 +457,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16x3": "bf16x3 (fp32-parity split, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}[mode],
+        "dtype": {"mixed": "bf16x3 coarse pass + fp16 fine pass (tcgen05 kind::f16, fp32 accumulate; fp32 parity bars)",
+                  "bf16x3": "bf16x3 (fp32-parity split, fp32 accumulate)", "bf16": "bf16", "fp16": "fp16", "fp32": "f32"}[mode],
         "data": "synthetic",
         "config": {"workload": "800x800 view render, 64+128 samples, random-init NeRF-W (BASELINE.json configs[1])",
                    "rays_per_step_per_gpu": n_rays, "mlp_evals_per_ray": SAMPLES_PER_RAY, "mlp_mode": mode,

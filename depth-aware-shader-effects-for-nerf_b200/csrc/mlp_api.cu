@@ -62,8 +62,9 @@ extern "C" int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const fl
       return launch_mlp_ffma_fwd(*w, src, app_off, total, raw, as_stream(stream));
     case NERFW_MLP_BF16X3:
     case NERFW_MLP_BF16:
+    case NERFW_MLP_FP16:
       NERFW_REQUIRE(packed, "nerfw_mlp_fwd: tensor-core modes need the packed weight cache (nerfw_pack_weights)");
-      return launch_mlp_tc_fwd(*w, packed, src, app_off, total, mode == NERFW_MLP_BF16X3, raw, relu_masks, as_stream(stream));
+      return launch_mlp_tc_fwd(*w, packed, src, app_off, total, mode, raw, relu_masks, as_stream(stream));
     default:
       set_error("nerfw_mlp_fwd: unknown mode %d", mode);
       return NERFW_EINVAL;

@@ -15,6 +15,7 @@
 // NERFW_MLP_BF16X3 ("fp32 parity" mode): every operand is split x = hi + lo with hi = bf16(x), lo = bf16(x - hi) and
 // each product is three MMAs  A_hi W_hi + A_lo W_hi + A_hi W_lo  (dropped term ~2^-18): ~2^-16 relative error per
 // product against 2^-9 for plain bf16 and 2^-11 for TF32.  A_lo lives in TMEM columns [384,512).
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "mlp_common.cuh"
 #include "mlp_tc.cuh"
@@ -27,7 +28,8 @@ namespace tc {
 
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: state_dict fp32 [out,in] -> bf16 hi/lo chunks in the exact shared-memory image (128B swizzle)
-__global__ void __launch_bounds__(256) pack_weights_kernel(NerfwWeights w, uint8_t* __restrict__ packed) {
+__global__ void __launch_bounds__(256) pack_weights_kernel(NerfwWeights w, uint8_t* __restrict__ packed,
+                                                           uint8_t* __restrict__ packed_f16) {
   // one thread per (chunk, output row, 8-wide k group)
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t big_items = (int64_t)N_BIG * 256 * 8;
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(NerfwWeights w, uint8
     if (cs.layer == 8) { W = w.dir_w; K = 256 + NERFW_DIR_DIM; }
     else { W = w.pts_w[cs.layer]; K = cs.layer == 0 ? NERFW_POS_DIM : (cs.layer == NERFW_SKIP ? 256 + NERFW_POS_DIM : 256); }
     __align__(16) __nv_bfloat16 hi[8], lo[8];
+    __align__(16) __half hf[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int col = cs.col0 + g * 8 + e;
@@ -58,12 +61,14 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(NerfwWeights w, uint8
       __nv_bfloat16 h = __float2bfloat16_rn(v);
       hi[e] = h;
       lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+      hf[e] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
     }
     const uint32_t sz = chunk < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
     uint8_t* base = packed + chunk_offset(chunk);
     uint32_t off = sw128_offset((uint32_t)n, (uint32_t)g * 8);
     *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(base + sz + off) = *reinterpret_cast<const uint4*>(lo);
+    if (packed_f16) *reinterpret_cast<uint4*>(packed_f16 + chunk_offset_f16(chunk) + off) = *reinterpret_cast<const uint4*>(hf);
   }
   // vector block
   float* vec = reinterpret_cast<float*>(packed + W_BYTES);
@@ -121,11 +126,14 @@ constexpr int F_EPI_THREADS = F_EPI_WARPS * 32;
 // profiling: event stamps (clock64) of CTA 0, third tile: slot -> time.  Only when a timeline buffer is passed.
 #define NERFW_STAMP(slot) do { if (timeline && blockIdx.x == 0 && tile == (int64_t)(2 * gridDim.x)) timeline[slot] = clock64(); } while (0)
 
-template <bool X3>
+// X3: split (three-MMA) arithmetic; F16 (with X3 = false): operands in fp16 instead of bf16 (11-bit significand, activations
+// saturate at 65504) from the fp16 weight image at packed + f16_offset.
+template <bool X3, bool F16 = false>
 __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* __restrict__ packed, SampleSource src,
                                                                  const float4* __restrict__ app_off, int64_t n_total,
                                                                  float4* __restrict__ raw, uint32_t* __restrict__ masks, int debug_skip_weights,
-                                                                 long long* __restrict__ timeline) {
+                                                                 long long* __restrict__ timeline, size_t f16_offset) {
+  static_assert(!(X3 && F16), "the fp16 mode is single pass");
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -191,7 +199,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
               mbar_arrive(&full[p.stage]);   // profiling only: reuse whatever the stage holds (results are wrong)
             } else {
               mbar_arrive_expect_tx(&full[p.stage], sz);
-              bulk_g2s(sm + RING + p.stage * BIG_CHUNK, packed + off + (size_t)v * sz, sz, &full[p.stage]);
+              const uint8_t* srcw = F16 ? packed + f16_offset + chunk_offset_f16(i) : packed + off + (size_t)v * sz;
+              bulk_g2s(sm + RING + p.stage * BIG_CHUNK, srcw, sz, &full[p.stage]);
             }
             p.advance();
           }
@@ -203,7 +212,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     // ===================== MMA issuer =====================
     if (lane == 0) {
       RingPipe p;
-      const uint32_t idesc256 = idesc_bf16(128, 256), idesc128 = idesc_bf16(128, 128);
+      const uint32_t idesc256 = F16 ? idesc_f16(128, 256) : idesc_bf16(128, 256);
+      const uint32_t idesc128 = F16 ? idesc_f16(128, 128) : idesc_bf16(128, 128);
       const uint32_t ring = smem_u32(sm + RING);
       const uint32_t d_acc = tmem + COL_ACC;
       // one 64-wide K block: A (hi[,lo]) x W chunk (hi[,lo]); a_* are either TMEM addresses (TS) or smem descs (SS)
@@ -300,11 +310,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         if (sr < n_total) src.position(sr, x);
         float v[32];
         if (cq == 0) {
-          pos_features32<0, !X3>(x, v);
-          store_features32<X3>(pex_hi, pex_lo, row, 0, v);
+          pos_features32<0, !X3 && !F16>(x, v);
+          store_features32<X3, F16>(pex_hi, pex_lo, row, 0, v);
         } else {
-          pos_features32<1, !X3>(x, v);
-          store_features32<X3>(pex_hi, pex_lo, row, 32, v);
+          pos_features32<1, !X3 && !F16>(x, v);
+          store_features32<X3, F16>(pex_hi, pex_lo, row, 32, v);
         }
       }
       fence_proxy_async_smem();
@@ -316,9 +326,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         float d[3] = {0.f, 0.f, 0.f};
         if (sr < n_total) src.direction(sr, d);
         float v[32];
-        dir_features32<!X3>(d, v);
+        dir_features32<!X3 && !F16>(d, v);
         if (dir_split) store_features32<true>(ped_hi, sm + SM_PED_LO, row, 0, v);
-        else store_features32<false>(ped_hi, ped_hi, row, 0, v);
+        else store_features32<false, F16>(ped_hi, ped_hi, row, 0, v);
         fence_proxy_async_smem();   // ordered before this warp's later a_kb arrivals, which the MMA thread waits on
       }
     };
@@ -359,8 +369,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
             const float4 bb = b4[j4];
             unpack2f(add2(pack2(r[kb][4 * j4], r[kb][4 * j4 + 1]), pack2f(bb.x, bb.y)), a[4 * j4], a[4 * j4 + 1]);
             unpack2f(add2(pack2(r[kb][4 * j4 + 2], r[kb][4 * j4 + 3]), pack2f(bb.z, bb.w)), a[4 * j4 + 2], a[4 * j4 + 3]);
-            ph[2 * j4] = relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
-            ph[2 * j4 + 1] = relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
+            ph[2 * j4] = F16 ? relu_pack_f16x2(a[4 * j4], a[4 * j4 + 1]) : relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
+            ph[2 * j4 + 1] = F16 ? relu_pack_f16x2(a[4 * j4 + 2], a[4 * j4 + 3]) : relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
           }
           tmem_st8(tlane + COL_AHI + apos, ph);
           if (want_lo) {  // lo = bf16(relu(a) - hi)
@@ -533,7 +543,8 @@ size_t mlp_tc_packed_bytes() { return tc::PACKED_BYTES; }
 
 int launch_pack_weights(const NerfwWeights& w, void* packed, cudaStream_t stream) {
   const int64_t total = (int64_t)tc::N_BIG * 256 * 8 + (int64_t)tc::N_SMALL * 128 * 8;
-  tc::pack_weights_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(packed));
+  tc::pack_weights_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(
+      w, reinterpret_cast<uint8_t*>(packed), reinterpret_cast<uint8_t*>(packed) + mlp_tc_packed_f16_offset());
   NERFW_LAUNCHED();
   return NERFW_OK;
 }
@@ -545,12 +556,14 @@ int launch_app_offset(const NerfwWeights& w, const float* emb, int64_t emb_rows,
 }
 
 int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSource& src, const float* app_off,
-                      int64_t n_total, bool x3, float* raw, void* relu_masks, cudaStream_t stream) {
+                      int64_t n_total, int mode, float* raw, void* relu_masks, cudaStream_t stream) {
+  const bool x3 = mode == NERFW_MLP_BF16X3, f16 = mode == NERFW_MLP_FP16;
   (void)w;
   static thread_local unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
   }
   int64_t ntiles = ceil_div64(n_total, tc::TM);
   int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
@@ -559,10 +572,15 @@ int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSou
   long long* timeline = nullptr;                              // profiling switch: device pointer (decimal) to 128 int64 slots
   if (const char* t = getenv("NERFW_FWD_TIMELINE")) timeline = reinterpret_cast<long long*>(strtoull(t, nullptr, 10));
   const float4* ao = reinterpret_cast<const float4*>(app_off);
+  const size_t f16_off = mlp_tc_packed_f16_offset();
+  float4* out = reinterpret_cast<float4*>(raw);
+  uint32_t* mk = reinterpret_cast<uint32_t*>(relu_masks);
   if (x3)
-    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks), dbg, timeline);
+    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
+  else if (f16)
+    tc::mlp_tc_fwd_kernel<false, true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
   else
-    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, reinterpret_cast<float4*>(raw), reinterpret_cast<uint32_t*>(relu_masks), dbg, timeline);
+    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
   NERFW_LAUNCHED();
   return NERFW_OK;
 }

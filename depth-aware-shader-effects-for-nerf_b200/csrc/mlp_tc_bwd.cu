@@ -30,7 +30,8 @@ using namespace tc;
 constexpr int NT_CHUNKS = 30;
 constexpr size_t WT_BYTES = (size_t)NT_CHUNKS * BIG_CHUNK;
 constexpr size_t PACKED_T_OFFSET = (PACKED_BYTES + 1023) & ~(size_t)1023;
-constexpr size_t PACKED_TOTAL = PACKED_T_OFFSET + WT_BYTES;
+constexpr size_t PACKED_F16_OFFSET = PACKED_T_OFFSET + WT_BYTES;
+constexpr size_t PACKED_TOTAL = PACKED_F16_OFFSET + F16_BYTES;
 
 // ---- scratch tile layout: 16 KB blocks [128 samples][64 features] bf16, 128B swizzle ------------------------------------
 constexpr uint32_t BLK = 16384;
@@ -987,6 +988,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int mode, int N, int 
 }  // namespace tcb
 
 size_t mlp_tc_packed_total_bytes() { return tcb::PACKED_TOTAL; }
+size_t mlp_tc_packed_f16_offset() { return tcb::PACKED_F16_OFFSET; }
 
 int launch_pack_weights_t(const NerfwWeights& w, void* packed, cudaStream_t stream) {
   const int64_t total = (int64_t)tcb::NT_CHUNKS * 256 * 8;

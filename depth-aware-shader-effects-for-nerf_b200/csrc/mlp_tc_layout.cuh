@@ -32,6 +32,11 @@ constexpr int V_DENB = 2816;    // 1
 constexpr int V_RGBB = 2817;    // 3
 constexpr int V_FLOATS = 2824;  // padded to 16 B
 constexpr size_t PACKED_BYTES = W_BYTES + V_FLOATS * sizeof(float);
+// fp16 copy of the forward image (single-pass fp16 mode), one copy per chunk, appended after the transposed image
+constexpr size_t F16_BYTES = N_BIG * (size_t)BIG_CHUNK + N_SMALL * (size_t)SMALL_CHUNK;
+__host__ __device__ inline size_t chunk_offset_f16(int i) {
+  return i < N_BIG ? (size_t)i * BIG_CHUNK : (size_t)N_BIG * BIG_CHUNK + (size_t)(i - N_BIG) * SMALL_CHUNK;
+}
 
 // TMEM columns
 constexpr uint32_t COL_ACC = 0;
@@ -118,6 +123,13 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo_elem, float hi_ele
   return r;
 }
 
+// the same to fp16, saturating (F2FP.SATFINITE.RELU.F16)
+__device__ __forceinline__ uint32_t relu_pack_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+
 // ---- positional encodings of one sample row, 32 consecutive features at a time (src/models.py:35-44) ---------------
 // Feature k of the 64-wide position tile: k < 3: x_k; k = 3 + 6 l + c: sin(2^l x_c); k = 6 + 6 l + c: cos(2^l x_c); 63: 0.
 // FAST (bf16 mode): level 0 by sincosf, higher levels by angle doubling (abs. error ~2^l ulp <= 1e-4, far below the bf16
@@ -188,7 +200,7 @@ __device__ __forceinline__ void dir_features32(const float (&d)[3], float (&v)[3
   }
 }
 // 32 features of one row -> K-major swizzled operand tile(s): four 16-byte stores per copy
-template <bool X3>
+template <bool X3, bool F16 = false>
 __device__ __forceinline__ void store_features32(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t row, uint32_t k0, const float (&v)[32]) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -196,7 +208,7 @@ __device__ __forceinline__ void store_features32(uint8_t* tile_hi, uint8_t* tile
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float a = v[8 * c + 2 * j], b = v[8 * c + 2 * j + 1];
-      h[j] = pack_bf16x2(a, b);
+      h[j] = F16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
       if (X3) l[j] = pack_bf16x2(a - __uint_as_float(h[j] << 16), b - __uint_as_float(h[j] & 0xffff0000u));
     }
     const uint32_t off = sw128_offset(row, k0 + 8 * c);

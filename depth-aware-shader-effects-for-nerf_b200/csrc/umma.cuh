@@ -106,6 +106,10 @@ __device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
 __device__ __host__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// same with A = B = fp16 (format code 0)
+__device__ __host__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 // ---- MMA ---------------------------------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]^T   (both K-major)
@@ -165,6 +169,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+// {fp16(lo_elem), fp16(hi_elem)}, saturating to the largest finite fp16 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);  // .x (low 16 bits) = lo_elem
   return *reinterpret_cast<uint32_t*>(&v);

@@ -10,8 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libnerfw_sm100.so")
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
 N_LAYERS = 8
-MLP_FP32, MLP_BF16X3, MLP_BF16 = 0, 1, 2
-MODE_NAMES = {"fp32": MLP_FP32, "bf16x3": MLP_BF16X3, "bf16": MLP_BF16}
+MLP_FP32, MLP_BF16X3, MLP_BF16, MLP_FP16 = 0, 1, 2, 3
+MODE_NAMES = {"fp32": MLP_FP32, "bf16x3": MLP_BF16X3, "bf16": MLP_BF16, "fp16": MLP_FP16}
 
 c_float_p = C.c_void_p  # device pointers are passed as integers
 

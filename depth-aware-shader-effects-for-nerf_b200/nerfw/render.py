@@ -18,9 +18,9 @@ from .autograd import RenderFn
 from .models import NeRF, resolve_mode
 
 
-def _shade(model: NeRF, o, d, z, emb, mode):
+def _shade(model: NeRF, o, d, z, emb, mode, role="single"):
     """(rgb (B,3), depth (B,1), acc (B,1), weights (B,N)) for given depths -- src/render.py:29-80."""
-    mode_id = resolve_mode(mode or model.mlp_mode)
+    mode_id = resolve_mode(mode or model.mlp_mode, role)
     names, tensors = model.kernel_params()
     ops.require_device(o.device)
     packed = model.packed_weights(names, tensors) if mode_id != 0 else None
@@ -61,15 +61,16 @@ def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
     if perturb:
         tr = t_rand.to(dev).reshape(b, n_samples) if t_rand is not None else torch.rand((b, n_samples), device=dev, generator=generator)
     z, _ = ops.stratified(None, None, ztab, tr, b, want_pts=False)         # src/render.py:22 (pts never materialised)
-    rgb, depth, acc, w = _shade(coarse, o, d, z, emb, mlp_dtype)
+    hier = n_importance > 0 and fine_pass
+    rgb, depth, acc, w = _shade(coarse, o, d, z, emb, mlp_dtype, "coarse" if hier else "single")
     extras = {}
-    if n_importance > 0 and fine_pass:
+    if hier:
         ur = u_rand.to(dev).reshape(b, n_importance) if u_rand is not None else torch.rand((b, n_importance), device=dev, generator=generator)
         z_all = ops.sample_pdf(z, w.detach(), int(n_importance), ur)       # src/ray_utils.py:90-149
         extras.update({"rgb_coarse": rgb.reshape(*orig_shape[:-1], 3), "depth_coarse": depth.reshape(*orig_shape[:-1], 1),
                        "acc_coarse": acc, "weights_coarse": w.unsqueeze(-1), "z_vals_coarse": z})
         z = z_all
-        rgb, depth, acc, w = _shade(fine, o, d, z, emb, mlp_dtype)
+        rgb, depth, acc, w = _shade(fine, o, d, z, emb, mlp_dtype, "fine")
     extras.update({"weights": w.unsqueeze(-1), "z_vals": z, "acc": acc})
     rgb_map = rgb.reshape(*orig_shape[:-1], 3)
     depth_map = depth.reshape(*orig_shape[:-1], 1)

@@ -39,7 +39,9 @@ enum {
 enum {
   NERFW_MLP_FP32 = 0,     /* CUDA-core fp32 FFMA; closest to the reference's fp32 nn.Linear */
   NERFW_MLP_BF16X3 = 1,   /* tcgen05 kind::f16, operands split hi+lo bf16, 3 MMAs per product (~2^-16 rel) */
-  NERFW_MLP_BF16 = 2      /* tcgen05 kind::f16, single bf16 MMA (stated looser bounds) */
+  NERFW_MLP_BF16 = 2,     /* tcgen05 kind::f16, single bf16 MMA (stated looser bounds) */
+  NERFW_MLP_FP16 = 3      /* tcgen05 kind::f16, single fp16 MMA: 8x finer operands than bf16, activations saturate at
+                             65504; the fine pass of the default hierarchical render (coarse pass in BF16X3) */
 };
 
 /* Architecture constants the kernels are specialised for (config.py:10-33 defaults). */

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 # max-abs bounds on (rgb, sigma) of one MLP evaluation at random init (|sigma| ~ 0.1, rgb ~ 0.5).  In bf16x3 inference the
 # direction layer (which only feeds the rgb sigmoid) runs as a single bf16 MMA: per-sample rgb 7e-5, sigma stays 1e-7.
-FWD_TOL = {"fp32": (2e-6, 2e-6), "bf16x3": (5e-4, 2e-5), "bf16": (8e-3, 8e-3)}
+FWD_TOL = {"fp32": (2e-6, 2e-6), "bf16x3": (5e-4, 2e-5), "bf16": (8e-3, 8e-3), "fp16": (1.5e-3, 1.5e-3)}
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -41,7 +41,7 @@ def test_umma_mn_major_primitive(n, k):
     assert err <= 1e-3, err
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16", "fp16"])
 def test_mlp_forward_golden(cuda_model, golden, mode):
     model, emb = cuda_model
     g = golden("mlp_64")
@@ -61,7 +61,7 @@ def test_mlp_forward_golden(cuda_model, golden, mode):
     assert e["rgb"] <= tr and e["rgb_noemb"] <= tr and e["sigma"] <= ts and e["sigma_noemb"] <= ts, e
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16", "fp16"])
 def test_mlp_forward_shapes_and_embeddings(cuda_model, oracle, state_dict, mode):
     """ragged sizes (not multiples of the 64/128-sample tiles), (D,), (1,D) and per-sample (S,D) embeddings."""
     model, emb = cuda_model
