@@ -32,8 +32,8 @@ def test_host_only_entry_points():
     assert L.nerfw_abi_version() == 1
     # 35 weight chunks (30 x 32 KB + 5 x 16 KB), hi+lo copies, plus the fp32 vector block
     fwd = 2 * (30 * 32768 + 5 * 16384) + 2824 * 4
-    # + the transposed (dgrad) image: 30 chunks of 32 KB, 1024-aligned
-    assert L.nerfw_packed_bytes() == (fwd + 1023) // 1024 * 1024 + 30 * 32768
+    # + the transposed (dgrad) image: 30 chunks of 32 KB, 1024-aligned; + the fp16 forward image (one copy per chunk)
+    assert L.nerfw_packed_bytes() == (fwd + 1023) // 1024 * 1024 + 30 * 32768 + (30 * 32768 + 5 * 16384)
     assert L.nerfw_mlp_bwd_tc_workspace_bytes(4096, 64) == 4096 + (4096 * 64 // 128) * 71 * 16384
     assert L.nerfw_mlp_workspace_bytes(4096, 1) >= 16
     assert L.nerfw_mlp_workspace_bytes(4096, 4096) >= 16 * 4096
