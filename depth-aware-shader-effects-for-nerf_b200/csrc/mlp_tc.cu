@@ -310,10 +310,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         if (sr < n_total) src.position(sr, x);
         float v[32];
         if (cq == 0) {
-          pos_features32<0, !X3 && !F16>(x, v);
+          pos_features32<0, !X3>(x, v);
           store_features32<X3, F16>(pex_hi, pex_lo, row, 0, v);
         } else {
-          pos_features32<1, !X3 && !F16>(x, v);
+          pos_features32<1, !X3>(x, v);
           store_features32<X3, F16>(pex_hi, pex_lo, row, 32, v);
         }
       }
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         float d[3] = {0.f, 0.f, 0.f};
         if (sr < n_total) src.direction(sr, d);
         float v[32];
-        dir_features32<!X3 && !F16>(d, v);
+        dir_features32<!X3>(d, v);
         if (dir_split) store_features32<true>(ped_hi, sm + SM_PED_LO, row, 0, v);
         else store_features32<false, F16>(ped_hi, ped_hi, row, 0, v);
         fence_proxy_async_smem();   // ordered before this warp's later a_kb arrivals, which the MMA thread waits on

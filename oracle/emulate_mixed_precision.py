@@ -1,0 +1,112 @@
+"""TEST INFRASTRUCTURE (CPU, oracle only): which operand precision does each pass of the hierarchical render need?
+
+Emulates the operand rounding of the tensor-core modes inside the oracle's MLP (products in float64 of the rounded
+operands, so only the operand format differs) and prints the max / mean abs error of rgb, depth and acc against the
+fp32 oracle for every (coarse pass, fine pass) combination, on a 48 x 48 crop of the golden view, random init and two
+dense variants.  Evidence for the `mixed` default: the error of the cheap modes comes from the
+coarse pass (it places the fine samples); a single fp16 MMA per product in the fine pass matches the bf16x3 split.
+
+    python oracle/emulate_mixed_precision.py            # ~10 min on 16 cores
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import nerfw_oracle as orc  # noqa: E402
+
+F = torch.nn.functional
+
+
+def rnd(t, dt):
+    return t.to(dt).to(torch.float32)
+
+
+def split(t, dt):
+    hi = rnd(t, dt)
+    return hi, rnd(t - hi, dt)
+
+
+def make_linear(scheme):
+    def lin(x, w, b):
+        xd, wd = x.double(), w.double()
+        if scheme == "fp32":
+            y = xd @ wd.T
+        elif scheme in ("bf16", "fp16"):
+            dt = torch.bfloat16 if scheme == "bf16" else torch.float16
+            y = rnd(x, dt).double() @ rnd(w, dt).double().T
+        elif scheme == "bf16x3":
+            xh, xl = split(x, torch.bfloat16)
+            wh, wl = split(w, torch.bfloat16)
+            y = xh.double() @ wh.double().T + xl.double() @ wh.double().T + xh.double() @ wl.double().T
+        elif scheme == "fp16_x1_w2":      # fp16 activations x split fp16 weights (2 MMAs)
+            wh, wl = split(w, torch.float16)
+            y = rnd(x, torch.float16).double() @ (wh.double() + wl.double()).T
+        elif scheme == "fp16_x2_w1":      # split fp16 activations x fp16 weights (2 MMAs)
+            xh, xl = split(x, torch.float16)
+            y = (xh.double() + xl.double()) @ rnd(w, torch.float16).double().T
+        else:
+            raise ValueError(scheme)
+        return (y + b.double()).float()
+    return lin
+
+
+def mlp(sd, x, d, emb, lin):
+    enc_x, enc_d = orc.encode(x, orc.POS_LEVELS), orc.encode(d, orc.DIR_LEVELS)
+    h = enc_x
+    for i in range(8):
+        if i == 4:
+            h = torch.cat([h, enc_x], -1)
+        h = F.relu(lin(h, sd[f"pts_linears.{i}.weight"], sd[f"pts_linears.{i}.bias"]))
+    sigma = F.relu(F.linear(h, sd["density_head.weight"], sd["density_head.bias"]))
+    hd = F.relu(lin(torch.cat([h, enc_d], -1), sd["dir_linear.weight"], sd["dir_linear.bias"]))
+    hd = hd + F.linear(emb.reshape(1, -1), sd["appearance_projection.weight"], sd["appearance_projection.bias"])
+    return torch.sigmoid(F.linear(hd, sd["rgb_linear.weight"], sd["rgb_linear.bias"])), sigma
+
+
+def render(sd, o, d, emb, coarse, fine, u):
+    b = o.shape[0]
+    z, _ = orc.stratified_depths(o, d, 2.0, 6.0, 64, perturb=False)
+
+    def shade(z, lin):
+        n = z.shape[1]
+        pts = o[:, None] + d[:, None] * z[..., None]
+        dirs = d[:, None].expand(-1, n, -1).reshape(-1, 3)
+        rgb, sig = mlp(sd, pts.reshape(-1, 3), dirs, emb, lin)
+        return orc.composite(sig.reshape(b, n, 1), rgb.reshape(b, n, 3), z)
+    _, _, wc = shade(z, make_linear(coarse))
+    z_all, _ = orc.resample_pdf(o, d, z, wc.squeeze(-1), 128, u_rand=u)
+    rf, df, wf = shade(z_all, make_linear(fine))
+    return rf, df, wf.sum(1)
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    h = w = 48
+    _, _, focal, c2w = orc.golden_camera(h, w)
+    ro, rd = orc.rays_for_view(h, w, focal, c2w)
+    o, d = ro.reshape(-1, 3).contiguous(), F.normalize(rd.reshape(-1, 3), dim=-1)
+    g = torch.Generator().manual_seed(5)
+    u = torch.rand(o.shape[0], 128, generator=g)
+    emb = torch.randn(32, generator=g)
+    combos = [("bf16x3", "bf16x3"), ("bf16x3", "fp16"), ("bf16x3", "bf16"), ("fp16", "bf16x3"), ("bf16", "bf16x3"),
+              ("bf16", "bf16"), ("fp16", "fp16"), ("fp16_x1_w2", "fp16_x1_w2"), ("fp16_x2_w1", "fp16_x2_w1")]
+    for variant in ("random-init", "dense x200", "dense x30"):
+        sd = orc.make_state_dict(0)
+        if variant != "random-init":
+            k = float(variant.split("x")[1])
+            sd["density_head.weight"] = sd["density_head.weight"] * k
+            sd["density_head.bias"] = sd["density_head.bias"] + 1.0
+        ref = render(sd, o, d, emb, "fp32", "fp32", u)
+        print(f"{variant}: mean acc {float(ref[2].mean()):.3f}")
+        for coarse, fine in combos:
+            got = render(sd, o, d, emb, coarse, fine, u)
+            e = [float((a - b).abs().max()) for a, b in zip(got, ref)]
+            m = [float((a - b).abs().mean()) for a, b in zip(got, ref)]
+            print(f"  coarse {coarse:11s} fine {fine:11s} max rgb {e[0]:.2e} depth {e[1]:.2e} acc {e[2]:.2e} | "
+                  f"mean rgb {m[0]:.1e} depth {m[1]:.1e} acc {m[2]:.1e}")
+
+
+if __name__ == "__main__":
+    main()

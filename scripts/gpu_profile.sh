@@ -16,18 +16,18 @@ BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $BENCH > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv $BENCH > gpurun_out/ncu_bench.log 2>&1
 echo "bench launch list rc=$?"
-for MODE in bf16x3 bf16; do
+for MODE in mixed bf16; do
   python scripts/profile_frame.py --mode $MODE --rows 200 > gpurun_out/pf_$MODE.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:'mlp_tc_fwd|composite_fwd|sample_pdf|stratified|raygen|normalize' \
       -o gpurun_out/prof_frame_$MODE -f python scripts/profile_frame.py --mode $MODE --rows 200 > gpurun_out/ncu_frame_$MODE.log 2>&1
   echo "frame $MODE rc=$?"
   export_rep prof_frame_$MODE mlp_tc_fwd
 done
-python scripts/profile_train.py bf16x3 1 > gpurun_out/pt.log 2>&1 &&
+python scripts/profile_train.py mixed 1 > gpurun_out/pt.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'pass1|wgrad|composite_bwd|adam|mse|app_' \
-    -o gpurun_out/prof_train -f python scripts/profile_train.py bf16x3 1 > gpurun_out/ncu_train_full.log 2>&1
+    -o gpurun_out/prof_train -f python scripts/profile_train.py mixed 1 > gpurun_out/ncu_train_full.log 2>&1
 echo "train rc=$?"
 export_rep prof_train pass1 wgrad
-python scripts/profile_train.py bf16x3 2 > gpurun_out/pt2.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train.csv python scripts/profile_train.py bf16x3 2 > gpurun_out/ncu_train_l.log 2>&1
+python scripts/profile_train.py mixed 2 > gpurun_out/pt2.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train.csv python scripts/profile_train.py mixed 2 > gpurun_out/ncu_train_l.log 2>&1
 du -sh gpurun_out; ls -la gpurun_out | head -40

@@ -25,7 +25,7 @@ def write(name, text):
 
 
 CMD = "`ncu --set full --clock-control none --import-source on -k regex:... python scripts/{}` (scripts/gpu_profile.sh)"
-for mode in ("bf16x3", "bf16"):
+for mode in ("mixed", "bf16x3", "bf16"):
     raw = os.path.join(OUT, f"prof_frame_{mode}_raw.csv")
     if os.path.exists(raw):
         write(f"{TAG}_ncu_full_{mode}.md",

@@ -17,7 +17,7 @@ from config import Config  # noqa: E402
 from nerfw.camera import aligned_spiral_poses, blender_focal  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--mode", default="bf16x3")
+ap.add_argument("--mode", default="mixed")
 ap.add_argument("--rows", type=int, default=800)
 ap.add_argument("--reps", type=int, default=1)
 args = ap.parse_args()

@@ -13,7 +13,7 @@ z = torch.sort(torch.rand(b, n, device="cuda", generator=g) * 4 + 2, dim=-1).val
 names, tensors = m.kernel_params()
 params = {k: t.detach() for k, t in zip(names, tensors)}
 packed = m.packed_weights(names, tensors)
-for mode, name in ((2, "bf16"), (1, "bf16x3")):
+for mode, name in ((2, "bf16"), (3, "fp16"), (1, "bf16x3")):
     for _ in range(2):
         ops.mlp_fwd(params, packed, o, d, z, None, mode)
     torch.cuda.synchronize()
