@@ -358,6 +358,17 @@ def selftest_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     return d
 
 
+def selftest_umma_2cta(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
+    """D = A B^T for A (256,K), B (N,K) bf16 through one CTA-pair (cta_group::2) MMA chain on a 2-CTA cluster."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[0] == 256 and a.shape[1] == b.shape[1]
+    a = a.contiguous()
+    b = b.contiguous()
+    d = torch.empty((256, b.shape[0]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().nerfw_selftest_umma_2cta(a.data_ptr(), b.data_ptr(), b.shape[0], a.shape[1], int(mode), d.data_ptr(), _stream()))
+    return d
+
+
 # ---- depth-aware effects (SURVEY.md 8f N3) --------------------------------------------------------------------------
 def _u8c(x: torch.Tensor, name: str) -> torch.Tensor:
     if x.dtype != torch.uint8 or not x.is_cuda:

@@ -224,6 +224,8 @@ int nerfw_hologram(const uint8_t* image, const float* mag, const float* mag_max,
 /* Primitive self-test (tests only): D (128,n) fp32 = A (128,k) bf16 * B (n,k) bf16 ^T through one tcgen05 tile;
  * mode 0 = A from shared memory, 1 = A from tensor memory.  Pins the descriptor / swizzle / TMEM layouts. */
 int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream);
+/* CTA-pair form (tcgen05 cta_group::2 on a 2-CTA cluster): D (256,n) = A (256,k) * B (n,k)^T, B split by n over the pair. */
+int nerfw_selftest_umma_2cta(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream);
 /* Same with both operands MN-major (the wgrad form): D (128,n) = At^T Bt for At (k,128), Bt (k,n) bf16 row-major. */
 int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, int n, int k, float* d, void* stream);
 /* Tensor-pipe issue-rate probe: device cycles (int64 at cycles_dev) for reps x 16 MMAs of shape 128 x n x 16;

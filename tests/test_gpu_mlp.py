@@ -256,3 +256,31 @@ def test_training_forward_keeps_split_direction_layer(cuda_model, golden):
     record("mlp_fwd_golden_bf16x3_training", rgb=e_rgb, sigma=e_sig)
     assert e_rgb <= 2e-5 and e_sig <= 2e-5, (e_rgb, e_sig)
     assert masks.numel() == 9 * 128 * 8 * 4
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "bf16x3"])
+def test_cta_pair_forward_kernel_bitwise_equal(cuda_model, monkeypatch, mode):
+    """The opt-in CTA-pair forward kernel (NERFW_FWD_PAIR=1: tcgen05 cta_group::2, M = 256 over two SMs, B split by N,
+    peer-CTA epilogues signalling the leader's mbarriers through the cluster) returns the same bits as the default kernel,
+    including an odd tile count (the pair's second tile past the end) and a ragged last tile."""
+    import nerfw
+    from nerfw import ops
+    model, emb = cuda_model
+    names, tensors = model.kernel_params()
+    params = {k: t.detach() for k, t in zip(names, tensors)}
+    packed = model.packed_weights(names, tensors)
+    mode_id = nerfw.models.resolve_mode(mode)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for b, n in ((400, 192), (399, 97)):          # 600 tiles; 302.4 -> 303 tiles (odd, ragged)
+        o = torch.randn(b, 3, device="cuda", generator=g)
+        d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda", generator=g), dim=-1)
+        z = torch.sort(torch.rand(b, n, device="cuda", generator=g) * 4 + 2, dim=-1).values
+        monkeypatch.delenv("NERFW_FWD_PAIR", raising=False)
+        want, wmask = ops.mlp_fwd(params, packed, o, d, z, emb.reshape(1, -1), mode_id, want_masks=True)
+        monkeypatch.setenv("NERFW_FWD_PAIR", "1")
+        got, gmask = ops.mlp_fwd(params, packed, o, d, z, emb.reshape(1, -1), mode_id, want_masks=True)
+        monkeypatch.delenv("NERFW_FWD_PAIR")
+        assert torch.equal(got, want)
+        # gate words: [tile][layer 0..8][row][8 words]; the direction layer (8) only writes words 0, 1, 4, 5
+        gm, wm = gmask.view(torch.int32).view(-1, 9, 128, 8), wmask.view(torch.int32).view(-1, 9, 128, 8)
+        assert torch.equal(gm[:, :8], wm[:, :8]) and torch.equal(gm[:, 8][..., [0, 1, 4, 5]], wm[:, 8][..., [0, 1, 4, 5]])
