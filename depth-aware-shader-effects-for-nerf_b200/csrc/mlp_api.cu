@@ -56,6 +56,8 @@ extern "C" int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const fl
     if (rc) return rc;
     app_off = reinterpret_cast<const float*>(workspace);
   }
+  const int mode_flags = mode;
+  mode &= 0xff;   // NERFW_MLP_SIGMA_ONLY rides in the upper bits
   switch (mode) {
     case NERFW_MLP_FP32:
       NERFW_REQUIRE(!relu_masks, "nerfw_mlp_fwd: relu_masks are produced by the tensor-core modes only");
@@ -64,7 +66,8 @@ extern "C" int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const fl
     case NERFW_MLP_BF16:
     case NERFW_MLP_FP16:
       NERFW_REQUIRE(packed, "nerfw_mlp_fwd: tensor-core modes need the packed weight cache (nerfw_pack_weights)");
-      return launch_mlp_tc_fwd(*w, packed, src, app_off, total, mode, raw, relu_masks, as_stream(stream));
+      NERFW_REQUIRE(!(mode_flags & NERFW_MLP_SIGMA_ONLY) || !relu_masks, "nerfw_mlp_fwd: NERFW_MLP_SIGMA_ONLY is an inference flag (no relu_masks)");
+      return launch_mlp_tc_fwd(*w, packed, src, app_off, total, mode_flags, raw, relu_masks, as_stream(stream));
     default:
       set_error("nerfw_mlp_fwd: unknown mode %d", mode);
       return NERFW_EINVAL;

@@ -136,9 +136,15 @@ constexpr int F_EPI_THREADS = F_EPI_WARPS * 32;
 template <bool X3, bool F16 = false, bool PAIR = false>
 __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t* __restrict__ packed, SampleSource src,
                                                                  const float4* __restrict__ app_off, int64_t n_total,
-                                                                 float4* __restrict__ raw, uint32_t* __restrict__ masks, int debug_skip_weights,
+                                                                 float4* __restrict__ raw, uint32_t* __restrict__ masks, int flags,
                                                                  long long* __restrict__ timeline, size_t f16_offset) {
   static_assert(!(X3 && F16), "the fp16 mode is single pass");
+  // flags: 1 = profiling, reuse whatever the ring holds after the first tile (wrong results); 2 = sigma only: the
+  // direction layer and the rgb head are skipped and raw = (0, 0, 0, sigma) -- all the coarse pass of a hierarchical
+  // inference render needs (its weights place the fine samples; its colour is never looked at)
+  const int debug_skip_weights = flags & 1;
+  const bool sigma_only = (flags & 2) != 0;
+  const int n_chunks = sigma_only ? N_BIG : N_CHUNKS;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       RingPipe p;
       for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
         size_t off = 0;
-        for (int i = 0; i < N_CHUNKS; ++i) {
+        for (int i = 0; i < n_chunks; ++i) {
           const uint32_t sz = i < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
           const uint32_t part = PAIR ? sz / 2 : sz;   // this CTA's rows of the chunk (B is split by N over the pair)
           const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       if (lane == 0) {
         RingPipe p;
         for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
-          for (int i = 0; i < N_CHUNKS; ++i) {
+          for (int i = 0; i < n_chunks; ++i) {
             const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
             for (int v = 0; v < copies; ++v) {
               mbar_wait(&full[p.stage], p.phase);
@@ -331,6 +337,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           commit(acc_full);
           NERFW_STAMP(13 + layer * 8);       // all MMAs of the layer issued
         }
+        if (sigma_only) continue;
         wait_bar(acc_free, ph_free);
         ph_free ^= 1;
         for (int kb = 0; kb < 4; ++kb) {
@@ -426,8 +433,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
             ph[2 * j4] = F16 ? relu_pack_f16x2(a[4 * j4], a[4 * j4 + 1]) : relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
             ph[2 * j4 + 1] = F16 ? relu_pack_f16x2(a[4 * j4 + 2], a[4 * j4 + 3]) : relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
           }
-          tmem_st8(tlane + COL_AHI + apos, ph);
-          if (want_lo) {  // lo = bf16(relu(a) - hi)
+          const bool publish = !(sigma_only && layer == NERFW_LAYERS - 1);   // nobody consumes layer 7's operand then
+          if (publish) tmem_st8(tlane + COL_AHI + apos, ph);
+          if (want_lo && publish) {  // lo = bf16(relu(a) - hi)
             uint32_t pl[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -452,19 +460,29 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
               sig = fmaf(fmaxf(a[4 * j4 + 2], 0.f), ww.z, sig); sig = fmaf(fmaxf(a[4 * j4 + 3], 0.f), ww.w, sig);
             }
           }
-          tmem_wait_st();
-          tc_fence_before();
-          arrive_leader(&a_kb[kb]);
+          if (publish) {
+            tmem_wait_st();
+            tc_fence_before();
+            arrive_leader(&a_kb[kb]);
+          }
           if (tid == 0 && kb == 0) NERFW_STAMP(16 + layer * 8);
           if (tid == 0 && kb == 3) NERFW_STAMP(17 + layer * 8);
         }
         if (layer == NERFW_SKIP + 1) {
-          encode_dir(tile);
+          if (!sigma_only) encode_dir(tile);
           if (base + tstride < ntiles) encode_pos(tile + tstride);
           if (tid == 0) NERFW_STAMP(90);   // encodings written
         }
       }
       sig_part[cq * TM + row] = sig;
+      if (sigma_only) {
+        named_bar_sync(1, F_EPI_THREADS);
+        if (cq == 0 && live) {
+          const float sg = (sig_part[row] + sig_part[TM + row]) + (sig_part[2 * TM + row] + sig_part[3 * TM + row]) + vec[V_DENB];
+          raw[s] = make_float4(0.f, 0.f, 0.f, fmaxf(sg, 0.f));
+        }
+        continue;
+      }
 
       // ---- direction-layer epilogue + rgb head (src/models.py:141-160) ----
       mbar_wait(acc_full, acc_phase);
@@ -697,7 +715,8 @@ int launch_app_offset(const NerfwWeights& w, const float* emb, int64_t emb_rows,
 }
 
 int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSource& src, const float* app_off,
-                      int64_t n_total, int mode, float* raw, void* relu_masks, cudaStream_t stream) {
+                      int64_t n_total, int mode_flags, float* raw, void* relu_masks, cudaStream_t stream) {
+  const int mode = mode_flags & 0xff;
   const bool x3 = mode == NERFW_MLP_BF16X3, f16 = mode == NERFW_MLP_FP16;
   (void)w;
   static thread_local unsigned long long attr_mask = 0;
@@ -709,7 +728,8 @@ int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSou
   int64_t ntiles = ceil_div64(n_total, tc::TM);
   int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
-  const int dbg = getenv("NERFW_FWD_SKIP_WEIGHTS") ? 1 : 0;  // profiling switch: time the kernel without L2 weight traffic
+  // kernel flags: bit 0 profiling switch (time the kernel without L2 weight traffic), bit 1 sigma-only output
+  const int dbg = (getenv("NERFW_FWD_SKIP_WEIGHTS") ? 1 : 0) | ((mode_flags & NERFW_MLP_SIGMA_ONLY) ? 2 : 0);
   long long* timeline = nullptr;                              // profiling switch: device pointer (decimal) to 128 int64 slots
   if (const char* t = getenv("NERFW_FWD_TIMELINE")) timeline = reinterpret_cast<long long*>(strtoull(t, nullptr, 10));
   const float4* ao = reinterpret_cast<const float4*>(app_off);

@@ -225,9 +225,10 @@ def pack_weights(params: dict, out: Optional[torch.Tensor] = None) -> torch.Tens
 
 
 def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: torch.Tensor, z: Optional[torch.Tensor],
-            emb: Optional[torch.Tensor], mode: int, want_masks: bool = False):
+            emb: Optional[torch.Tensor], mode: int, want_masks: bool = False, sigma_only: bool = False):
     """raw (S,4) = (r,g,b,sigma).  p,d: (B,3) rays with z (B,N), or (S,3) samples with z None.
-    want_masks (tensor-core modes): also return the ReLU gate words for nerfw_mlp_bwd_tc -> (raw, masks)."""
+    want_masks (tensor-core modes): also return the ReLU gate words for nerfw_mlp_bwd_tc -> (raw, masks).
+    sigma_only (tensor-core modes, inference): NERFW_MLP_SIGMA_ONLY -- raw = (0, 0, 0, sigma), direction layer skipped."""
     dev = p.device
     n_rays = p.shape[0]
     n_samples = z.shape[1] if z is not None else 1
@@ -244,7 +245,7 @@ def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: to
         masks = torch.empty(int(lib().nerfw_mlp_mask_bytes(n_rays, n_samples)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         check(lib().nerfw_mlp_fwd(C.byref(ws), _ptr(packed), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows,
-                                  n_rays, n_samples, int(mode), raw.data_ptr(), _ptr(masks), ws_buf.data_ptr(), wbytes,
+                                  n_rays, n_samples, int(mode) | (0x100 if sigma_only and int(mode) != 0 else 0), raw.data_ptr(), _ptr(masks), ws_buf.data_ptr(), wbytes,
                                   _stream()))
     if want_masks:
         return raw, masks

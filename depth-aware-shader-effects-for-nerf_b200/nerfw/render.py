@@ -18,7 +18,7 @@ from .autograd import RenderFn
 from .models import NeRF, resolve_mode
 
 
-def _shade(model: NeRF, o, d, z, emb, mode, role="single"):
+def _shade(model: NeRF, o, d, z, emb, mode, role="single", sigma_only=False):
     """(rgb (B,3), depth (B,1), acc (B,1), weights (B,N)) for given depths -- src/render.py:29-80."""
     mode_id = resolve_mode(mode or model.mlp_mode, role)
     names, tensors = model.kernel_params()
@@ -30,19 +30,21 @@ def _shade(model: NeRF, o, d, z, emb, mode, role="single"):
     if needs_grad:
         return RenderFn.apply(mode_id, names, o, d, z, emb, packed, *tensors)
     raw = ops.mlp_fwd({n: t.detach() for n, t in zip(names, tensors)}, packed, o, d, z,
-                      None if emb is None else emb.detach(), mode_id)
+                      None if emb is None else emb.detach(), mode_id, sigma_only=sigma_only)
     return ops.composite_fwd(raw, z, want_weights=True)
 
 
 def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
                   appearance_embedding=None, background_color=None, perturb=True, *,
                   mlp_dtype: Optional[str] = None, fine_pass: Optional[bool] = None, generator=None,
-                  t_rand=None, u_rand=None):
+                  t_rand=None, u_rand=None, coarse_rgb: Optional[bool] = None):
     """Returns (rgb_map (...,3), depth_map (...,1), extras) like src/render.py:92-97.
 
     `background_color` is accepted and ignored, as in the reference (src/render.py:6).  `t_rand` (B,N) / `u_rand`
     (B,NI) inject the uniforms the reference draws at src/ray_utils.py:80 and :119 (otherwise torch.rand on the device,
-    in that order)."""
+    in that order).  `coarse_rgb`: whether the coarse pass of a hierarchical render also evaluates colour
+    (extras['rgb_coarse']); default: only when gradients are recorded (the training loss uses it) -- for inference the
+    coarse pass only has to place the fine samples, so its direction layer and rgb head are skipped."""
     coarse, fine = (model if isinstance(model, (tuple, list)) else (model, model))
     if fine_pass is None:
         fine_pass = os.environ.get("NERFW_COARSE_ONLY", "0") != "1"
@@ -62,13 +64,18 @@ def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
         tr = t_rand.to(dev).reshape(b, n_samples) if t_rand is not None else torch.rand((b, n_samples), device=dev, generator=generator)
     z, _ = ops.stratified(None, None, ztab, tr, b, want_pts=False)         # src/render.py:22 (pts never materialised)
     hier = n_importance > 0 and fine_pass
-    rgb, depth, acc, w = _shade(coarse, o, d, z, emb, mlp_dtype, "coarse" if hier else "single")
+    if coarse_rgb is None:
+        coarse_rgb = torch.is_grad_enabled()
+    sigma_only = hier and not coarse_rgb and not torch.is_grad_enabled()
+    rgb, depth, acc, w = _shade(coarse, o, d, z, emb, mlp_dtype, "coarse" if hier else "single", sigma_only)
     extras = {}
     if hier:
         ur = u_rand.to(dev).reshape(b, n_importance) if u_rand is not None else torch.rand((b, n_importance), device=dev, generator=generator)
         z_all = ops.sample_pdf(z, w.detach(), int(n_importance), ur)       # src/ray_utils.py:90-149
-        extras.update({"rgb_coarse": rgb.reshape(*orig_shape[:-1], 3), "depth_coarse": depth.reshape(*orig_shape[:-1], 1),
+        extras.update({"depth_coarse": depth.reshape(*orig_shape[:-1], 1),
                        "acc_coarse": acc, "weights_coarse": w.unsqueeze(-1), "z_vals_coarse": z})
+        if not sigma_only:
+            extras["rgb_coarse"] = rgb.reshape(*orig_shape[:-1], 3)
         z = z_all
         rgb, depth, acc, w = _shade(fine, o, d, z, emb, mlp_dtype, "fine")
     extras.update({"weights": w.unsqueeze(-1), "z_vals": z, "acc": acc})

@@ -43,6 +43,9 @@ enum {
   NERFW_MLP_FP16 = 3      /* tcgen05 kind::f16, single fp16 MMA: 8x finer operands than bf16, activations saturate at
                              65504; the fine pass of the default hierarchical render (coarse pass in BF16X3) */
 };
+/* OR into `mode` (tensor-core modes, inference): skip the direction layer and the rgb head, raw = (0, 0, 0, sigma).  All the
+ * coarse pass of a hierarchical render needs: its weights place the fine samples, its colour is never looked at. */
+#define NERFW_MLP_SIGMA_ONLY 0x100
 
 /* Architecture constants the kernels are specialised for (config.py:10-33 defaults). */
 #define NERFW_HIDDEN 256

@@ -284,3 +284,35 @@ def test_cta_pair_forward_kernel_bitwise_equal(cuda_model, monkeypatch, mode):
         # gate words: [tile][layer 0..8][row][8 words]; the direction layer (8) only writes words 0, 1, 4, 5
         gm, wm = gmask.view(torch.int32).view(-1, 9, 128, 8), wmask.view(torch.int32).view(-1, 9, 128, 8)
         assert torch.equal(gm[:, :8], wm[:, :8]) and torch.equal(gm[:, 8][..., [0, 1, 4, 5]], wm[:, 8][..., [0, 1, 4, 5]])
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "fp16", "bf16"])
+def test_sigma_only_flag(cuda_model, oracle, mode):
+    """NERFW_MLP_SIGMA_ONLY: same sigma bits as the full forward, rgb = 0; and the hierarchical render is bit-identical
+    whether the coarse pass evaluates colour or not (inference default: it does not)."""
+    import nerfw
+    from nerfw import ops
+    model, emb = cuda_model
+    names, tensors = model.kernel_params()
+    params = {k: t.detach() for k, t in zip(names, tensors)}
+    packed = model.packed_weights(names, tensors)
+    mode_id = nerfw.models.resolve_mode(mode)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for b, n in ((37, 64), (300, 129)):
+        o = torch.randn(b, 3, device="cuda", generator=g)
+        d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda", generator=g), dim=-1)
+        z = torch.sort(torch.rand(b, n, device="cuda", generator=g) * 4 + 2, dim=-1).values
+        full = ops.mlp_fwd(params, packed, o, d, z, emb.reshape(1, -1), mode_id)
+        sig = ops.mlp_fwd(params, packed, o, d, z, emb.reshape(1, -1), mode_id, sigma_only=True)
+        assert torch.equal(sig[:, 3], full[:, 3]) and float(sig[:, :3].abs().max()) == 0.0
+    h, w, focal, c2w = oracle.golden_camera()
+    ro, rd = nerfw.get_rays(h, w, focal, c2w.cuda())
+    oc, dc = ro[40:60, 40:60].reshape(-1, 3), rd[40:60, 40:60].reshape(-1, 3)
+    u = torch.rand(400, 128, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        a = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, appearance_embedding=emb, perturb=False, mlp_dtype=mode, u_rand=u)
+        bb = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, appearance_embedding=emb, perturb=False, mlp_dtype=mode, u_rand=u,
+                                 coarse_rgb=True)
+    assert "rgb_coarse" not in a[2] and "rgb_coarse" in bb[2]
+    assert torch.equal(a[0], bb[0]) and torch.equal(a[1], bb[1]) and torch.equal(a[2]["z_vals"], bb[2]["z_vals"])
+    assert torch.equal(a[2]["depth_coarse"], bb[2]["depth_coarse"])
