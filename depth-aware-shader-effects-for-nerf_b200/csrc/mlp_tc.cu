@@ -124,9 +124,6 @@ constexpr int F_THREADS = 576;
 constexpr int F_EPI_THREADS = F_EPI_WARPS * 32;
 
 // profiling: event stamps (clock64) of CTA 0, third tile: slot -> time.  Only when a timeline buffer is passed.
-// STAMP_USE: the ring-stage use (running index) whose recycle latency is stamped: commit -> stage free seen by the producer
-// -> refill landed (slots 110-114).
-constexpr int STAMP_USE = 90;
 #define NERFW_STAMP(slot) do { if (timeline && blockIdx.x == 0 && (tile == (int64_t)(2 * gridDim.x) || tile == (int64_t)(2 * (gridDim.x & ~1u)))) timeline[slot] = clock64(); } while (0)
 
 // X3: split (three-MMA) arithmetic; F16 (with X3 = false): operands in fp16 instead of bf16 (11-bit significand, activations
@@ -220,7 +217,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     // ===================== weight producer =====================
     if (lane == 0) {
       RingPipe p;
-      int use_idx = 0;   // profiling: running index of ring-stage uses
       for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
         size_t off = 0;
         for (int i = 0; i < n_chunks; ++i) {
@@ -228,10 +224,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           const uint32_t part = PAIR ? sz / 2 : sz;   // this CTA's rows of the chunk (B is split by N over the pair)
           const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
           for (int v = 0; v < copies; ++v) {
-            if (timeline && blockIdx.x == 0 && use_idx == STAMP_USE + STAGES) timeline[111] = clock64();   // producer starts waiting
             mbar_wait(&empty[p.stage], p.phase ^ 1);
-            if (timeline && blockIdx.x == 0 && use_idx == STAMP_USE + STAGES) timeline[112] = clock64();   // ... stage seen free
-            ++use_idx;
             if (debug_skip_weights && tile != tile0) {
               mbar_arrive(&full[p.stage]);   // profiling only: reuse whatever the stage holds (results are wrong)
             } else {
@@ -277,16 +270,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       auto commit = [&](uint64_t* bar) {
         if (PAIR) mma_commit_2cta(bar); else mma_commit(bar);
       };
-      long long wait_cycles = 0;   // profiling: cycles this thread spent waiting for weight stages (timeline runs only)
-      int use_idx = 0;
       auto wait_stage = [&]() {
-        const long long w0 = timeline ? clock64() : 0;
         mbar_wait(&full[p.stage], p.phase);
-        if (timeline) {
-          const long long w1 = clock64();
-          wait_cycles += w1 - w0;
-          if (blockIdx.x == 0 && use_idx == STAMP_USE + STAGES) { timeline[113] = w0; timeline[114] = w1; }   // next use of the stage: wait start / refill landed
-        }
         if (PAIR) mbar_wait(&pfull[p.stage], p.phase);   // remote arrivals are release.cluster; the plain wait is what CUTLASS' ClusterBarrier uses
         tc_fence_after();
       };
@@ -308,8 +293,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           }
         }
         commit(&empty[p.stage]);
-        if (timeline && blockIdx.x == 0 && use_idx == STAMP_USE) timeline[110] = clock64();   // MMAs of this stage issued + committed
-        ++use_idx;
         p.advance();
         if (split) {
           wait_stage();
@@ -319,7 +302,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
             else mma_s(d_acc, a_hi + 2 * k, bl + 2 * k, idesc, 1u);
           }
           commit(&empty[p.stage]);
-          ++use_idx;
           p.advance();
         }
       };
@@ -354,7 +336,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           }
           commit(acc_full);
           NERFW_STAMP(13 + layer * 8);       // all MMAs of the layer issued
-          if (timeline && blockIdx.x == 0 && (tile == (int64_t)(2 * gridDim.x) || tile == (int64_t)(2 * (gridDim.x & ~1u)))) timeline[100 + layer] = wait_cycles;
         }
         if (sigma_only) continue;
         wait_bar(acc_free, ph_free);

@@ -29,6 +29,3 @@ for layer in range(8):
     print(f"layer {layer}: " + "  ".join(f"{k}={v}" for k, v in row))
 for slot, name in ((90, "epi: encodings for next tile written"), (91, "epi: dir acc complete seen"), (92, "epi: dir acc in regs"), (93, "epi: tile written")):
     print(f"{name}: {t[slot] - t0 if t[slot] else None}")
-print("cumulative cycles the MMA thread waited for weight stages, after each layer:", [t[100 + l] for l in range(8)])
-print("ring-stage recycle (cycles after the commit of use 90): producer began waiting %d, saw the stage free %d, MMA thread began waiting for the refill %d, refill landed %d"
-      % tuple(t[s] - t[110] for s in (111, 112, 113, 114)))
