@@ -157,9 +157,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   };
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
-  uint64_t* a_ready = acc_full + 1;
   // per-K-block operand barriers, accumulator-free and encodings-ready barriers (one arrival per epilogue warp)
-  uint64_t* a_kb = a_ready + 1;
+  uint64_t* a_kb = acc_full + 2;
   uint64_t* acc_free = a_kb + 4;
   uint64_t* pe_ready = acc_free + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM_TMEMPTR);
@@ -530,9 +529,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_pair_kernel(const uin
   uint64_t* empty = full + STAGES;
   uint64_t* pfull = empty + STAGES;                    // PAIR, leader: the peer CTA's half of the stage has landed
   uint64_t* acc_full = pfull + (PAIR ? STAGES : 0);
-  uint64_t* a_ready = acc_full + 1;
   // per-K-block operand barriers, accumulator-free and encodings-ready barriers (one arrival per epilogue warp)
-  uint64_t* a_kb = a_ready + 1;
+  uint64_t* a_kb = acc_full + 2;
   uint64_t* acc_free = a_kb + 4;
   uint64_t* pe_ready = acc_free + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM_TMEMPTR);
@@ -634,36 +632,34 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_pair_kernel(const uin
       const uint32_t ring = smem_u32(sm + RING);
       const uint32_t d_acc = tmem + COL_ACC;
       // one 64-wide K block: A (hi[,lo]) x W chunk (hi[,lo]); a_* are either TMEM addresses (TS) or smem descs (SS)
-      // (no helper lambdas in here: captured-by-reference state would leave the uniform datapath and every descriptor /
-      // barrier address of this latency-critical thread would need an R2UR -- measured -3 % on the whole kernel)
-#define NERFW_MMA_T(d, a, b, idesc, accf) do { if constexpr (PAIR) mma_ts_2cta(d, a, b, idesc, accf); else mma_ts(d, a, b, idesc, accf); } while (0)
-#define NERFW_MMA_S(d, a, b, idesc, accf) do { if constexpr (PAIR) mma_ss_2cta(d, a, b, idesc, accf); else mma_ss(d, a, b, idesc, accf); } while (0)
-#define NERFW_COMMIT(bar) do { if constexpr (PAIR) mma_commit_2cta(bar); else mma_commit(bar); } while (0)
-#define NERFW_WAIT_STAGE() do { mbar_wait(&full[p.stage], p.phase); if constexpr (PAIR) mbar_wait(&pfull[p.stage], p.phase); tc_fence_after(); } while (0)
       auto kblock = [&](bool from_tmem, uint64_t a_hi, uint64_t a_lo, uint32_t idesc, int ksteps, bool first, bool split = X3) {
-        NERFW_WAIT_STAGE();
+        mbar_wait(&full[p.stage], p.phase);
+        mbar_wait(&pfull[p.stage], p.phase);   // the peer CTA's half (relayed)
+        tc_fence_after();
         uint64_t b = smem_desc_sw128(ring + p.stage * STAGE_BYTES);
         for (int k = 0; k < ksteps; ++k) {
           uint32_t accf = (first && k == 0) ? 0u : 1u;
-          if (from_tmem) NERFW_MMA_T(d_acc, (uint32_t)a_hi + 8 * k, b + 2 * k, idesc, accf);
-          else NERFW_MMA_S(d_acc, a_hi + 2 * k, b + 2 * k, idesc, accf);
+          if (from_tmem) mma_ts_2cta(d_acc, (uint32_t)a_hi + 8 * k, b + 2 * k, idesc, accf);
+          else mma_ss_2cta(d_acc, a_hi + 2 * k, b + 2 * k, idesc, accf);
         }
         if (split) {
           for (int k = 0; k < ksteps; ++k) {
-            if (from_tmem) NERFW_MMA_T(d_acc, (uint32_t)a_lo + 8 * k, b + 2 * k, idesc, 1u);
-            else NERFW_MMA_S(d_acc, a_lo + 2 * k, b + 2 * k, idesc, 1u);
+            if (from_tmem) mma_ts_2cta(d_acc, (uint32_t)a_lo + 8 * k, b + 2 * k, idesc, 1u);
+            else mma_ss_2cta(d_acc, a_lo + 2 * k, b + 2 * k, idesc, 1u);
           }
         }
-        NERFW_COMMIT(&empty[p.stage]);
+        mma_commit_2cta(&empty[p.stage]);
         p.advance();
         if (split) {
-          NERFW_WAIT_STAGE();
+          mbar_wait(&full[p.stage], p.phase);
+        mbar_wait(&pfull[p.stage], p.phase);   // the peer CTA's half (relayed)
+        tc_fence_after();
           uint64_t bl = smem_desc_sw128(ring + p.stage * STAGE_BYTES);
           for (int k = 0; k < ksteps; ++k) {
-            if (from_tmem) NERFW_MMA_T(d_acc, (uint32_t)a_hi + 8 * k, bl + 2 * k, idesc, 1u);
-            else NERFW_MMA_S(d_acc, a_hi + 2 * k, bl + 2 * k, idesc, 1u);
+            if (from_tmem) mma_ts_2cta(d_acc, (uint32_t)a_hi + 8 * k, bl + 2 * k, idesc, 1u);
+            else mma_ss_2cta(d_acc, a_hi + 2 * k, bl + 2 * k, idesc, 1u);
           }
-          NERFW_COMMIT(&empty[p.stage]);
+          mma_commit_2cta(&empty[p.stage]);
           p.advance();
         }
       };
@@ -696,7 +692,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_pair_kernel(const uin
             ph_kb ^= 1;
             if (layer == NERFW_SKIP) kblock(false, pex_hi, pex_lo, idesc256, 4, false);
           }
-          NERFW_COMMIT(acc_full);
+          mma_commit_2cta(acc_full);
           NERFW_STAMP(13 + layer * 8);       // all MMAs of the layer issued
         }
         if (sigma_only) continue;
@@ -708,7 +704,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_pair_kernel(const uin
         }
         ph_kb ^= 1;
         kblock(false, ped_hi, ped_lo, idesc128, 2, false, dir_split);
-        NERFW_COMMIT(acc_full);
+        mma_commit_2cta(acc_full);
       }
     }
   } else {

@@ -131,30 +131,6 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int block0, uint32_t 
   }
 }
 
-// Same data through a per-warp 2 KB shared-memory staging buffer, so that four consecutive lanes write the 64 contiguous
-// bytes of one row: a warp store then touches 8 cache lines instead of 32 (scattered 16-byte stores cost one LSU cycle per
-// line and were the bottleneck of this kernel).  Slot rotation by row/2 keeps both the staging writes and reads at the
-// 4-wavefront minimum.  `stage` is this warp's buffer; only used when the mask region of shared memory is free.
-__device__ __forceinline__ void store_row32_staged(uint8_t* stage, uint8_t* tile, int block0, uint32_t row0, uint32_t lane,
-                                                   uint32_t col, const uint32_t (&p)[16]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t slot = (c + (lane >> 1)) & 3;
-    *reinterpret_cast<uint4*>(stage + lane * 64 + slot * 16) = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
-  }
-  __syncwarp();
-  uint8_t* blk = tile + (size_t)(block0 + (col >> 6)) * BLK;
-  const uint32_t k0 = col & 63;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t r = 8 * i + (lane >> 2), c = lane & 3;
-    const uint32_t slot = (c + (r >> 1)) & 3;
-    const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 64 + slot * 16);
-    *reinterpret_cast<uint4*>(blk + sw128_offset(row0 + r, k0 + 8 * c)) = v;
-  }
-  __syncwarp();
-}
-
 // ====================================================================================================================
 // profiling: clock64 stamps of CTA 0, third tile (slot = 16 + 8 * step + event); only when a timeline buffer is passed
 #define P1_STAMP(slot) do { if (timeline && blockIdx.x == 0 && tile == (int64_t)(2 * gridDim.x)) timeline[slot] = clock64(); } while (0)
