@@ -180,21 +180,30 @@ def run_reference(args):
     sd, emb = make_weights()
     pose = aligned_spiral_poses(120, 2, "x", "chair")[0]
     times = []
+    rays_done = 0
     n = 0
     cores = 1
+    rays_per_step = args.cpu_rays
+    budget_s = 180.0          # the whole --steps K --warmup W run stays within a few minutes whatever K and W are
     for i in range(args.warmup + args.steps):
-        n, dt, cores, _ = cpu_sample(sd, emb, args.cpu_rays, pose)
+        n, dt, cores, _ = cpu_sample(sd, emb, rays_per_step, pose)
         if i >= args.warmup:
             times.append(dt)
+            rays_done += n
+        if i == 0:   # size the remaining steps from the measured rate (whole rows of the view, at least 2 400 rays)
+            left = args.warmup + args.steps - 1
+            if left > 0 and dt * left > budget_s:
+                rays_per_step = max(2400, int(n * budget_s / (dt * left)) // 800 * 800)
     total = sum(times)
-    val = n * len(times) / total / 1e6
-    sample = f"{n} rays of the 800x800 view per step (centre rows), coarse 64 + fine 192, torch CPU ops == reference code path"
+    val = rays_done / total / 1e6
+    sample = (f"{n} rays of the 800x800 view per step (centre rows; {args.cpu_rays} in the first step), coarse 64 + fine 192, "
+              "torch CPU ops == reference code path")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "800x800 view render, 64+128 samples, random-init NeRF-W (BASELINE.json configs[1])",
-                   "rays_per_step": n, "note": "CPU reference path: rank 0 only, bounded sample per step"},
+                   "rays_per_step": n, "note": "CPU reference path: rank 0 only, bounded sample per step (sized to ~3 min per run)"},
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
