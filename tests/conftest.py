@@ -16,6 +16,15 @@ for p in (PKG, os.path.join(ROOT, "oracle")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA sm_100 (B200) device; run with -m gpu on the GPU box")
+    # The tests load the C-ABI library.  In a fresh checkout (the .so is git-ignored) build it first, exactly like
+    # __graft_entry__.build(); where nvcc is missing too the ABI tests fail loudly with the ImportError of nerfw._lib.
+    lib_path = os.path.join(PKG, "nerfw", "libnerfw_sm100.so")
+    if not os.path.exists(lib_path):
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            sys.path.insert(0, ROOT)
+            import __graft_entry__
+            __graft_entry__.build()
 
 
 def pytest_collection_modifyitems(config, items):
