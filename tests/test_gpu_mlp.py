@@ -316,3 +316,25 @@ def test_sigma_only_flag(cuda_model, oracle, mode):
     assert "rgb_coarse" not in a[2] and "rgb_coarse" in bb[2]
     assert torch.equal(a[0], bb[0]) and torch.equal(a[1], bb[1]) and torch.equal(a[2]["z_vals"], bb[2]["z_vals"])
     assert torch.equal(a[2]["depth_coarse"], bb[2]["depth_coarse"])
+
+
+def test_fp16_mode_saturates_instead_of_overflowing(state_dict):
+    """fp16 operands saturate at 65 504 (F2FP.SATFINITE): a network whose activations leave the fp16 range still gives
+    finite outputs in the fp16 / mixed modes (and the bf16x3 mode, which has the range of fp32, is unaffected)."""
+    import nerfw
+    from config import Config
+    sd, emb = state_dict
+    sd = {k: v.clone() for k, v in sd.items()}
+    sd["pts_linears.0.weight"] *= 3e4          # first-layer activations ~1e5
+    sd["pts_linears.1.weight"] *= 1e-4         # keep the rest of the trunk in range
+    m = nerfw.NeRF(Config())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = (torch.rand(777, 3, device="cuda", generator=g) - 0.5) * 6
+    d = torch.nn.functional.normalize(torch.randn(777, 3, device="cuda", generator=g), dim=-1)
+    with torch.no_grad():
+        for mode in ("fp16", "bf16x3"):
+            m.mlp_mode = mode
+            rgb, sigma = m(x, d, emb.cuda())
+            assert bool(torch.isfinite(rgb).all()) and bool(torch.isfinite(sigma).all()), mode
