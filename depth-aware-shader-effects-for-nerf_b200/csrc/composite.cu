@@ -248,6 +248,60 @@ __global__ void __launch_bounds__(CP_WARPS * 32) composite_bwd_reg_kernel(
   }
 }
 
+// Merge of the per-sample MLP outputs of the coarse samples (already evaluated in the coarse pass) and of the new fine
+// samples into the depth order of the merged row that sample_pdf produced: slot of coarse i = i + #{k : zf_k < z_i}, slot
+// of fine k = k + #{i : z_i <= zf_k} (coarse first on ties; tied samples sit at the same point, so their order is
+// immaterial).  One warp per ray, both depth lists in shared memory, fixed-length binary searches.  Used by the opt-in
+// `reuse_coarse` path of volume_render: when coarse and fine pass share one network, the fine pass only has to evaluate
+// the NI new samples instead of all N + NI.
+constexpr int MG_WARPS = 4;
+__global__ void __launch_bounds__(MG_WARPS * 32) merge_raw_kernel(const float* __restrict__ zc, const float4* __restrict__ rc,
+                                                                  const float* __restrict__ zf, const float4* __restrict__ rf,
+                                                                  int64_t B, int N, int NI, float4* __restrict__ out) {
+  extern __shared__ float mg_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sc = mg_smem + (size_t)warp * (N + NI);
+  float* sf = sc + N;
+  for (int64_t ray = (int64_t)blockIdx.x * MG_WARPS + warp; ray < B; ray += (int64_t)gridDim.x * MG_WARPS) {
+    for (int i = lane; i < N; i += 32) sc[i] = __ldg(zc + ray * N + i);
+    for (int k = lane; k < NI; k += 32) sf[k] = __ldg(zf + ray * NI + k);
+    __syncwarp();
+    float4* o = out + ray * (N + NI);
+    // both lists are sorted when they come from the renderer; a caller-injected u_rand can leave the fine list unsorted:
+    // such a ray is ranked by plain counting (stable: coarse before fine, lower index first on ties)
+    bool sorted = true;
+    for (int i = lane; i < N; i += 32) sorted = sorted && (i == 0 || sc[i - 1] <= sc[i]);
+    for (int k = lane; k < NI; k += 32) sorted = sorted && (k == 0 || sf[k - 1] <= sf[k]);
+    if (!__all_sync(0xffffffffu, sorted)) {
+      for (int e = lane; e < N + NI; e += 32) {
+        const bool is_c = e < N;
+        const float v = is_c ? sc[e] : sf[e - N];
+        int rank = 0;
+        for (int j = 0; j < N + NI; ++j) {
+          const float w = j < N ? sc[j] : sf[j - N];
+          rank += (w < v || (w == v && j < e)) ? 1 : 0;
+        }
+        o[rank] = is_c ? __ldg(rc + ray * N + e) : __ldg(rf + ray * NI + (e - N));
+      }
+      __syncwarp();
+      continue;
+    }
+    for (int i = lane; i < N; i += 32) {          // #{k : zf_k < z_i}: lower bound in the fine list
+      const float v = sc[i];
+      int lo = 0, hi = NI;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sf[mid] < v) lo = mid + 1; else hi = mid; }
+      o[i + lo] = __ldg(rc + ray * N + i);
+    }
+    for (int k = lane; k < NI; k += 32) {         // #{i : z_i <= zf_k}: upper bound in the coarse list
+      const float v = sf[k];
+      int lo = 0, hi = N;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sc[mid] <= v) lo = mid + 1; else hi = mid; }
+      o[k + lo] = __ldg(rf + ray * NI + k);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace nerfw
 
 using namespace nerfw;
@@ -289,6 +343,24 @@ extern "C" int nerfw_composite_bwd(const float* raw, const float* z, int64_t n_r
   else if (nchunks <= 6) launch(composite_bwd_reg_kernel<6>);   // 64 + 128
   else if (nchunks <= 8) launch(composite_bwd_reg_kernel<8>);
   else launch(composite_bwd_kernel);
+  NERFW_LAUNCHED();
+  return NERFW_OK;
+}
+
+extern "C" int nerfw_merge_raw(const float* z_coarse, const float* raw_coarse, const float* z_fine, const float* raw_fine,
+                               int64_t n_rays, int n_samples, int n_importance, float* raw_out, void* stream) {
+  NERFW_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_importance >= 1 && n_samples + n_importance <= 4096,
+                "nerfw_merge_raw: bad shape B=%lld N=%d NI=%d", (long long)n_rays, n_samples, n_importance);
+  if (n_rays == 0) return NERFW_OK;
+  NERFW_REQUIRE(z_coarse && raw_coarse && z_fine && raw_fine && raw_out, "nerfw_merge_raw: null pointer");
+  NERFW_REQUIRE(aligned16(raw_coarse) && aligned16(raw_fine) && aligned16(raw_out), "nerfw_merge_raw: raw buffers must be 16-byte aligned");
+  const size_t smem = (size_t)MG_WARPS * (n_samples + n_importance) * sizeof(float);
+  int64_t blocks = ceil_div64(n_rays, MG_WARPS);
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  merge_raw_kernel<<<(unsigned)blocks, MG_WARPS * 32, smem, as_stream(stream)>>>(
+      z_coarse, reinterpret_cast<const float4*>(raw_coarse), z_fine, reinterpret_cast<const float4*>(raw_fine), n_rays,
+      n_samples, n_importance, reinterpret_cast<float4*>(raw_out));
   NERFW_LAUNCHED();
   return NERFW_OK;
 }

@@ -124,7 +124,7 @@ def ray_points(rays_o: torch.Tensor, rays_d: torch.Tensor, z: torch.Tensor) -> t
 
 
 def sample_pdf(z_vals: torch.Tensor, weights: torch.Tensor, n_importance: int, u_rand: torch.Tensor,
-               want_aux: bool = False):
+               want_aux: bool = False, want_zfine: bool = False):
     z_vals = _f32c(z_vals, "z_vals")
     weights = _f32c(weights, "weights")
     u_rand = _f32c(u_rand, "u_rand")
@@ -140,12 +140,28 @@ def sample_pdf(z_vals: torch.Tensor, weights: torch.Tensor, n_importance: int, u
         inds = torch.empty((b, n_importance), dtype=torch.int64, device=dev)
         zf = torch.empty((b, n_importance), dtype=torch.float32, device=dev)
         cdf = torch.empty((b, n + 1), dtype=torch.float32, device=dev)
+    if want_zfine and zf is None:
+        zf = torch.empty((b, n_importance), dtype=torch.float32, device=dev)
     ulin = u_table(n_importance, dev)
     with torch.cuda.device(dev):
         check(lib().nerfw_sample_pdf(z_vals.data_ptr(), weights.data_ptr(), ulin.data_ptr(), u_rand.data_ptr(), b, n,
                                      int(n_importance), out.data_ptr(), _ptr(inds), _ptr(zf), _ptr(cdf), _stream()))
     if want_aux:
         return out, {"inds": inds, "z_fine": zf, "cdf": cdf}
+    if want_zfine:
+        return out, zf
+    return out
+
+
+def merge_raw(z_coarse: torch.Tensor, raw_coarse: torch.Tensor, z_fine: torch.Tensor, raw_fine: torch.Tensor) -> torch.Tensor:
+    """(B,N) / (B*N,4) coarse and (B,NI) / (B*NI,4) fine depths and MLP outputs -> raw (B*(N+NI),4) in merged depth order."""
+    b, n = z_coarse.shape
+    ni = z_fine.shape[1]
+    out = torch.empty((b * (n + ni), 4), dtype=torch.float32, device=z_coarse.device)
+    with torch.cuda.device(z_coarse.device):
+        check(lib().nerfw_merge_raw(_f32c(z_coarse, "z_coarse").data_ptr(), _f32c(raw_coarse, "raw_coarse").data_ptr(),
+                                    _f32c(z_fine, "z_fine").data_ptr(), _f32c(raw_fine, "raw_fine").data_ptr(), b, n, ni,
+                                    out.data_ptr(), _stream()))
     return out
 
 

@@ -34,17 +34,46 @@ def _shade(model: NeRF, o, d, z, emb, mode, role="single", sigma_only=False):
     return ops.composite_fwd(raw, z, want_weights=True)
 
 
+def _render_reusing_coarse(model: NeRF, o, d, z, emb, mode, n_importance, u_rand, generator, orig_shape, src_dev):
+    """Hierarchical inference render with one network: coarse pass on z (full outputs), resampling, fine pass on the NEW
+    depths only, merge of both sets of (r,g,b,sigma) records into depth order, compositing of the merged row."""
+    dev, b = o.device, o.shape[0]
+    names, tensors = model.kernel_params()
+    params = {n: t.detach() for n, t in zip(names, tensors)}
+    packed = model.packed_weights(names, tensors)
+    e = None if emb is None else emb.detach()
+    raw_c = ops.mlp_fwd(params, packed, o, d, z, e, resolve_mode(mode or model.mlp_mode, "coarse"))
+    rgb_c, depth_c, acc_c, w_c = ops.composite_fwd(raw_c, z, want_weights=True)
+    ur = u_rand.to(dev).reshape(b, n_importance) if u_rand is not None else torch.rand((b, n_importance), device=dev, generator=generator)
+    z_all, z_new = ops.sample_pdf(z, w_c, n_importance, ur, want_zfine=True)       # src/ray_utils.py:90-149
+    raw_f = ops.mlp_fwd(params, packed, o, d, z_new, e, resolve_mode(mode or model.mlp_mode, "fine"))
+    raw = ops.merge_raw(z, raw_c, z_new, raw_f)
+    rgb, depth, acc, w = ops.composite_fwd(raw, z_all, want_weights=True)
+    extras = {"rgb_coarse": rgb_c.reshape(*orig_shape[:-1], 3), "depth_coarse": depth_c.reshape(*orig_shape[:-1], 1),
+              "acc_coarse": acc_c, "weights_coarse": w_c.unsqueeze(-1), "z_vals_coarse": z,
+              "weights": w.unsqueeze(-1), "z_vals": z_all, "acc": acc}
+    rgb_map = rgb.reshape(*orig_shape[:-1], 3)
+    depth_map = depth.reshape(*orig_shape[:-1], 1)
+    if src_dev != dev:
+        rgb_map, depth_map = rgb_map.to(src_dev), depth_map.to(src_dev)
+        extras = {k: v.to(src_dev) for k, v in extras.items()}
+    return rgb_map, depth_map, extras
+
+
 def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
                   appearance_embedding=None, background_color=None, perturb=True, *,
                   mlp_dtype: Optional[str] = None, fine_pass: Optional[bool] = None, generator=None,
-                  t_rand=None, u_rand=None, coarse_rgb: Optional[bool] = None):
+                  t_rand=None, u_rand=None, coarse_rgb: Optional[bool] = None, reuse_coarse: Optional[bool] = None):
     """Returns (rgb_map (...,3), depth_map (...,1), extras) like src/render.py:92-97.
 
     `background_color` is accepted and ignored, as in the reference (src/render.py:6).  `t_rand` (B,N) / `u_rand`
     (B,NI) inject the uniforms the reference draws at src/ray_utils.py:80 and :119 (otherwise torch.rand on the device,
     in that order).  `coarse_rgb`: whether the coarse pass of a hierarchical render also evaluates colour
     (extras['rgb_coarse']); default: only when gradients are recorded (the training loss uses it) -- for inference the
-    coarse pass only has to place the fine samples, so its direction layer and rgb head are skipped."""
+    coarse pass only has to place the fine samples, so its direction layer and rgb head are skipped.
+    `reuse_coarse` (opt-in, or NERFW_REUSE_COARSE=1; inference with ONE network for both passes, as in the reference):
+    the fine pass evaluates only the n_importance new samples and re-uses the coarse pass's outputs at the n_samples
+    coarse depths (a third less MLP work in the fine pass; the outputs stay within the same parity bars)."""
     coarse, fine = (model if isinstance(model, (tuple, list)) else (model, model))
     if fine_pass is None:
         fine_pass = os.environ.get("NERFW_COARSE_ONLY", "0") != "1"
@@ -66,6 +95,11 @@ def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
     hier = n_importance > 0 and fine_pass
     if coarse_rgb is None:
         coarse_rgb = torch.is_grad_enabled()
+    if reuse_coarse is None:
+        reuse_coarse = os.environ.get("NERFW_REUSE_COARSE", "0") == "1"
+    reuse_coarse = bool(reuse_coarse) and hier and coarse is fine and not torch.is_grad_enabled()
+    if reuse_coarse:
+        return _render_reusing_coarse(coarse, o, d, z, emb, mlp_dtype, int(n_importance), u_rand, generator, orig_shape, src_dev)
     sigma_only = hier and not coarse_rgb and not torch.is_grad_enabled()
     rgb, depth, acc, w = _shade(coarse, o, d, z, emb, mlp_dtype, "coarse" if hier else "single", sigma_only)
     extras = {}

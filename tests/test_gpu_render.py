@@ -300,3 +300,33 @@ def test_odd_sample_counts_end_to_end(cuda_model, oracle, state_dict, n, ni):
     e = dict(rgb=maxabs(rgb, rgb_o), depth=maxabs(depth, depth_o), acc=maxabs(ex["acc"], ex_o["acc"]))
     record(f"odd_counts_{n}_{ni}", **e)
     assert e["rgb"] <= 1e-3 and e["depth"] <= 2e-3 and e["acc"] <= 1e-3, e
+
+
+def test_reuse_coarse_opt_in(cuda_model, oracle, golden):
+    """reuse_coarse=True (one network for both passes, inference): the fine pass evaluates only the 128 new samples and the
+    coarse outputs are merged in by depth.  In bf16x3 mode every sample is evaluated by the same kernel either way, so the
+    result is bit-identical to the default path; in the default mixed mode it stays inside the fp32 parity bars."""
+    import nerfw
+    model, emb = cuda_model
+    o, d = view(oracle)
+    g = golden("crop32_hier")
+    oc = o[34:66, 34:66].reshape(-1, 3)
+    dc = d[34:66, 34:66].reshape(-1, 3)
+    u = torch.from_numpy(g["u_rand"])
+    kw = dict(appearance_embedding=emb, perturb=False, u_rand=u)
+    with torch.no_grad():
+        ref = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", **kw)
+        got = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", reuse_coarse=True, **kw)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and torch.equal(got[2]["weights"], ref[2]["weights"])
+        assert torch.equal(got[2]["z_vals"], ref[2]["z_vals"])
+        mix = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="mixed", reuse_coarse=True, **kw)
+        e = dict(rgb=maxabs(mix[0], g["rgb"]), depth=maxabs(mix[1], g["depth"]), acc=maxabs(mix[2]["acc"], g["acc"]))
+        record("crop32_hier_mixed_reuse_coarse", **e)
+        assert e["rgb"] <= 1e-3 and e["depth"] <= 1e-3 and e["acc"] <= 1e-3, e
+        # injected uniforms outside [0,1): the fine list is not sorted, the merge ranks by counting
+        u_bad = u.clone()
+        u_bad[:64] *= 3.0
+        kw_bad = dict(appearance_embedding=emb, perturb=False, u_rand=u_bad)
+        ref_b = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", **kw_bad)
+        got_b = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", reuse_coarse=True, **kw_bad)
+        assert torch.equal(got_b[0], ref_b[0]) and torch.equal(got_b[1], ref_b[1])
