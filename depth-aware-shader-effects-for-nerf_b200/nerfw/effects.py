@@ -52,6 +52,16 @@ def toon(image: torch.Tensor, depth: torch.Tensor, levels: int = 5, edge_strengt
     return ops.toon(img, mag, mag_max, levels, edge_strength)
 
 
+_SCANLINE_CACHE: dict = {}
+
+
+def _scanline_table_on(device, height: int, num_lines: int) -> torch.Tensor:
+    key = (str(device), int(height), int(num_lines))
+    if key not in _SCANLINE_CACHE:
+        _SCANLINE_CACHE[key] = scanline_table(height, num_lines).to(device)
+    return _SCANLINE_CACHE[key]
+
+
 def scanline_table(height: int, num_lines: int = 50) -> torch.Tensor:
     """Per-row factor of the hologram scanlines, built with the reference's loop (src/post_processor.py:385-393)."""
     line_height = height / num_lines
@@ -78,4 +88,4 @@ def hologram(image: torch.Tensor, depth: Optional[torch.Tensor], num_lines: int 
         for x_pos, x_width in lines:
             hits_host[x_pos:min(x_pos + x_width, w)] += 1
         hits = hits_host.to(img.device)
-    return ops.hologram(img, mag, mag_max, scanline_table(h, num_lines).to(img.device), hits, noise)
+    return ops.hologram(img, mag, mag_max, _scanline_table_on(img.device, h, num_lines), hits, noise)
