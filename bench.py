@@ -8,6 +8,15 @@ A step = one synthetic 800x800 view (640 000 rays) rendered coarse(64) + fine(64
 rays in pinned HOST memory and the rgb/depth images read back to the host inside the timed region.
 Under torchrun (N > 1) every rank renders its own view of the aligned spiral (weak scaling, no data-path collective);
 time is the max over ranks.  One JSON line on stdout (rank 0).
+
+Further legs inside the same line (each in its own named field, none of them the headline):
+  spiral_120        BASELINE.json configs[3]: the 120-frame aligned spiral, frames round-robin over the ranks, per-frame
+                    device-to-host copy overlapped with the next frame, finished frames gathered to rank 0 (wall clock)
+  strong_one_frame  one 800x800 frame split into row blocks over the ranks + gather
+  dp_check          N > 1: all-reduced data-parallel gradient == single-GPU gradient of the concatenated batch
+  stress_256_512    BASELINE.json configs[4]: 4096 rays, 256 + 512 samples, bf16 MLP
+  eager_baseline    SURVEY.md 8(d) secondary baseline: the reference algorithm in PyTorch eager ON the B200
+  other_modes       two-pass (no coarse re-use), bf16x3, fp32 frame times; the reference's 4096-ray chunk loop
 """
 from __future__ import annotations
 
@@ -50,6 +59,8 @@ def parse_args():
     ap.add_argument("--cpu-rays", type=int, default=int(os.environ.get("NERFW_CPU_SAMPLE_RAYS", "24000")),
                     help="rays in the bounded CPU sample (cpu_baseline / --impl reference step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spiral-frames", type=int, default=120, help="frames of the config-4 leg (0 = skip)")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary legs (spiral, strong scaling, fp32 frame, eager)")
     return ap.parse_args()
 
 
@@ -141,6 +152,16 @@ def max_over_ranks(ms: float, world: int) -> float:
     return float(t.item())
 
 
+def camera_module():
+    """nerfw/camera.py executed on its own (numpy only): the CPU reference arm needs the spiral poses but must not import
+    the product package, whose __init__ loads libnerfw_sm100.so."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_nerfw_camera_standalone", os.path.join(PKG, "nerfw", "camera.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_weights():
     import nerfw_oracle as orc
     sd = orc.make_state_dict(0)          # == torch.manual_seed(0); NeRF(Config()) of the reference
@@ -148,21 +169,26 @@ def make_weights():
     return sd, emb
 
 
-def cpu_sample(sd, emb, n_rays: int, pose: np.ndarray):
+def cpu_sample(sd, emb, n_rays: int, pose: np.ndarray, strided: bool = False):
     """The reference algorithm (oracle port: same torch-CPU ops, same cost) on a bounded sample of the SAME workload:
-    `n_rays` rays from the centre rows of the 800x800 view, coarse 64 + fine 192, all host threads."""
+    `n_rays` rays of the 800x800 view -- the centre rows, or (strided) every k-th ray of the WHOLE frame so that image
+    borders and grazing rays are in the parity sample too -- coarse 64 + fine 192, all host threads."""
     import nerfw_oracle as orc
-    from nerfw.camera import blender_focal
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    focal = blender_focal(W)
+    focal = camera_module().blender_focal(W)
     c2w = torch.from_numpy(pose)
-    rows = max(1, n_rays // W)
-    r0 = H // 2 - rows // 2
-    # rays of the selected rows only (same formula as the full view; rays_for_view builds whole images)
     ro, rd = orc.rays_for_view(H, W, focal, c2w)
-    o = ro[r0:r0 + rows].reshape(-1, 3)[:n_rays].contiguous()
-    d = rd[r0:r0 + rows].reshape(-1, 3)[:n_rays].contiguous()
+    if strided:
+        step = max(1, (H * W) // n_rays)
+        sel = torch.arange(step // 2, H * W, step)[:n_rays]
+        o = ro.reshape(-1, 3)[sel].contiguous()
+        d = rd.reshape(-1, 3)[sel].contiguous()
+    else:
+        rows = max(1, n_rays // W)
+        r0 = H // 2 - rows // 2
+        o = ro[r0:r0 + rows].reshape(-1, 3)[:n_rays].contiguous()
+        d = rd[r0:r0 + rows].reshape(-1, 3)[:n_rays].contiguous()
     torch.manual_seed(1)
     u = torch.rand(o.shape[0], N_IMPORTANCE)
     t0 = time.perf_counter()
@@ -176,9 +202,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from nerfw.camera import aligned_spiral_poses
     sd, emb = make_weights()
-    pose = aligned_spiral_poses(120, 2, "x", "chair")[0]
+    pose = camera_module().aligned_spiral_poses(120, 2, "x", "chair")[0]
     times = []
     rays_done = 0
     n = 0
@@ -186,7 +211,7 @@ def run_reference(args):
     rays_per_step = args.cpu_rays
     budget_s = 180.0          # the whole --steps K --warmup W run stays within a few minutes whatever K and W are
     for i in range(args.warmup + args.steps):
-        n, dt, cores, _ = cpu_sample(sd, emb, rays_per_step, pose)
+        n, dt, cores, _ = cpu_sample(sd, emb, rays_per_step, pose, strided=True)
         if i >= args.warmup:
             times.append(dt)
             rays_done += n
@@ -196,7 +221,7 @@ def run_reference(args):
                 rays_per_step = max(2400, int(n * budget_s / (dt * left)) // 800 * 800)
     total = sum(times)
     val = rays_done / total / 1e6
-    sample = (f"{n} rays of the 800x800 view per step (centre rows; {args.cpu_rays} in the first step), coarse 64 + fine 192, "
+    sample = (f"{n} rays of the 800x800 view per step (every k-th ray; {args.cpu_rays} in the first step), coarse 64 + fine 192, "
               "torch CPU ops == reference code path")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -211,7 +236,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def bench_train_step(nerfw, sd, dev, world, mode, n_rays=4096, steps=6, warmup=2):
+def bench_train_step(nerfw, sd, dev, world, mode, n_rays=4096, steps=6, warmup=2, per_ray_emb=False):
     """BASELINE.json configs[2]: 4096-ray batch per GPU, coarse+fine forward/backward + Adam, data parallel (one
     all-reduce of the flat gradient buffer per step when world > 1).  Returns ms per step (max over ranks)."""
     from config import Config
@@ -225,19 +250,150 @@ def bench_train_step(nerfw, sd, dev, world, mode, n_rays=4096, steps=6, warmup=2
     o = torch.tensor([0.0, 0.0, 4.0], device=dev).expand(n_rays, 3).contiguous()
     d = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=dev, generator=g) * 0.3 + torch.tensor([0.0, 0.0, -1.0], device=dev), dim=-1)
     tgt = torch.rand(n_rays, 3, device=dev, generator=g)
+    img = torch.randint(0, 100, (n_rays,), device=dev, generator=g) if per_ray_emb else 3
     for _ in range(warmup):
-        tr.step(o, d, tgt, 3, NEAR, FAR, N_COARSE, N_IMPORTANCE, perturb=True, generator=g)
+        tr.step(o, d, tgt, img, NEAR, FAR, N_COARSE, N_IMPORTANCE, perturb=True, generator=g)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss = tr.step(o, d, tgt, 3, NEAR, FAR, N_COARSE, N_IMPORTANCE, perturb=True, generator=g)
+        loss = tr.step(o, d, tgt, img, NEAR, FAR, N_COARSE, N_IMPORTANCE, perturb=True, generator=g)
     e1.record()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1) / steps, world)
     return {"ms_per_step": ms, "rays_per_gpu": n_rays, "n_gpus": world, "samples": "64+128 (coarse+fine fwd/bwd) + Adam",
             "forward_mode": mode, "backward": "tcgen05 bf16 MLP backward (dgrad fused with forward recompute + MN-major wgrad), composite_bwd",
             "allreduce_bytes": int(tr.flat.grad.numel() * 4) if world > 1 else 0, "final_loss": float(loss)}
+
+
+def dp_check(nerfw, sd, dev, rank, world):
+    """N > 1: the data-parallel gradient (every rank backpropagates its contiguous slice of a global batch, one flat
+    all-reduce, 1/world) against the single-GPU gradient of the concatenated batch, fp32 mode, no jitter.  Returns the
+    max-abs difference relative to the largest gradient entry (<= 1e-6 rel up to atomics order)."""
+    import torch.distributed as dist
+    from config import Config
+    from nerfw.parallel import shard_bounds
+    b = 2048
+    g = torch.Generator(device=dev).manual_seed(99)        # same seed on every rank: the same global batch
+    o = torch.tensor([0.0, 0.0, 4.0], device=dev).expand(b, 3).contiguous()
+    d = torch.nn.functional.normalize(torch.randn(b, 3, device=dev, generator=g) * 0.3 + torch.tensor([0.0, 0.0, -1.0], device=dev), dim=-1)
+    tgt = torch.rand(b, 3, device=dev, generator=g)
+    emb = torch.randn(32, device=dev, generator=g)
+
+    def grad_of(lo, hi):
+        m = nerfw.NeRF(Config())
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev)
+        rgb, _, _ = nerfw.volume_render(m, o[lo:hi], d[lo:hi], NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb,
+                                        perturb=False, mlp_dtype="fp32", u_rand=u[lo:hi])
+        torch.nn.functional.mse_loss(rgb, tgt[lo:hi]).backward()
+        return torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+
+    u = torch.rand(b, N_IMPORTANCE, device=dev, generator=g)
+    s, e = shard_bounds(b, rank, world)
+    g_local = grad_of(s, e)
+    dist.all_reduce(g_local, op=dist.ReduceOp.SUM)
+    g_dp = g_local / world
+    g_full = grad_of(0, b)
+    rel = float((g_dp - g_full).abs().max() / g_full.abs().max())
+    t = torch.tensor([rel], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"rel_max_abs": float(t.item()), "bar": 1e-5, "ok": bool(float(t.item()) <= 1e-5), "global_batch": b, "mode": "fp32",
+            "what": "all-reduced flat gradient / world vs single-GPU gradient of the concatenated batch (equal shards, mean loss)"}
+
+
+def spiral_leg(nerfw, model, emb_d, dev, rank, world, mode, n_frames):
+    """BASELINE.json configs[3]: the aligned spiral (render_aligned_spiral.py:77-175), frames i -> rank i mod world.  Per
+    round every rank renders one frame (device-resident, uint8 quantisation on the device), the finished records (rgb8 +
+    fp32 depth, 4.48 MB per frame) are gathered to rank 0 over NCCL and rank 0 copies them to pinned host memory on a copy
+    stream while the next round renders.  Wall clock between two barriers, everything delivered."""
+    import torch.distributed as dist
+    from nerfw.camera import aligned_spiral_poses, blender_focal
+    from nerfw.frame import quantize_frame, render_frame
+    from nerfw.io import stage_to_host
+    poses = aligned_spiral_poses(n_frames, 2, "x", "chair")
+    focal = blender_focal(W)
+    copy_stream = torch.cuda.Stream(device=dev)
+    rec_bytes = H * W * 3 + H * W * 4
+    rounds = (n_frames + world - 1) // world
+    delivered = []
+
+    def one_round(r):
+        i = r * world + rank
+        rec = torch.zeros(rec_bytes, dtype=torch.uint8, device=dev)
+        if i < n_frames:
+            rgb, depth, _ = render_frame(model, H, W, focal, poses[i], NEAR, FAR, N_COARSE, N_IMPORTANCE,
+                                         appearance_embedding=emb_d, mlp_dtype=mode)
+            rgb8, _ = quantize_frame(rgb)
+            rec = torch.cat([rgb8.reshape(-1), depth.contiguous().view(torch.uint8).reshape(-1)])
+        if world > 1:
+            bufs = [torch.empty_like(rec) for _ in range(world)] if rank == 0 else None
+            dist.gather(rec, bufs, dst=0)
+        else:
+            bufs = [rec]
+        if rank == 0:
+            for k, bfr in enumerate(bufs):
+                if r * world + k < n_frames:
+                    delivered.append(stage_to_host(bfr, copy_stream))
+
+    one_round(0)                      # warm-up round (allocator, NCCL channels)
+    delivered.clear()
+    barrier(world)
+    t0 = time.perf_counter()
+    for r in range(rounds):
+        one_round(r)
+    for _, ev in delivered:
+        ev.synchronize()
+    barrier(world)
+    dt = time.perf_counter() - t0
+    ok = True
+    if rank == 0:
+        ok = len(delivered) == n_frames and all(int(h[: H * W * 3].max()) > 0 for h, _ in delivered[:2])
+    return {"frames": n_frames, "wall_s": dt, "value": n_frames * H * W / dt / 1e6, "unit": "Mrays/s", "n_gpus": world,
+            "frames_per_rank": rounds, "ms_per_frame_per_gpu": 1e3 * dt / rounds, "delivered_to_rank0_bytes": n_frames * rec_bytes,
+            "delivered_ok": bool(ok), "partition": "frame i -> rank i mod world; gather(rgb8 + depth fp32) to rank 0 each round; "
+            "D2H on a copy stream overlapped with the next round"}
+
+
+def strong_leg(nerfw, model, emb_d, dev, rank, world, mode, o_dev, d_dev, reps=3):
+    """One frame, rays split into contiguous row blocks over the ranks, (rgb, depth, acc) gathered (20 B per ray)."""
+    from nerfw.parallel import render_sharded
+
+    def fn(o, d):
+        with torch.no_grad():
+            return nerfw.volume_render(model, o, d, NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb_d,
+                                       perturb=False, mlp_dtype=mode)
+    render_sharded(fn, o_dev, d_dev, dst=0)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        render_sharded(fn, o_dev, d_dev, dst=0)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1) / reps, world)
+    return {"ms_per_frame": ms, "value": H * W / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "scaling": "strong",
+            "partition": f"{H * W // world} rays per rank (row blocks), all_gather of 20 B/ray records, result on rank 0"}
+
+
+def timed(fn, reps, world=1):
+    """ms per call of fn() (device time, CUDA events on the current stream, max over ranks), after one warm-up call."""
+    fn()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1) / reps, world)
+
+
+def parity_stats(got, want, bar=1e-3):
+    """max / 99.9th percentile abs error and the number of rays over the bar."""
+    e = (got.detach().cpu().double() - want.double()).abs().reshape(got.shape[0], -1).max(dim=1).values
+    k = max(1, int(0.999 * e.numel()))
+    return {"max_abs": float(e.max()), "p999_abs": float(e.kthvalue(k).values), "rays_over_bar": int((e > bar).sum())}
 
 
 def run_ours(args):
@@ -260,13 +416,14 @@ def run_ours(args):
     c2w = torch.from_numpy(pose)
     mode = args.mlp_mode
     n_rays = H * W
+    warmup = max(3, args.warmup)             # timing rules: never fewer than 3 warm-up steps; reported as used
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
 
-    def render(o, d):
+    def render(o, d, **kw):
         with torch.no_grad():
             return nerfw.volume_render(model, o, d, NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb_d,
-                                       perturb=False, mlp_dtype=mode, generator=gen)
+                                       perturb=False, mlp_dtype=kw.pop("mlp_dtype", mode), generator=gen, **kw)
 
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     ro, rd = nerfw.get_rays(H, W, focal, c2w.to(dev))
     o_dev = ro.reshape(-1, 3).contiguous()
     d_dev = rd.reshape(-1, 3).contiguous()
@@ -284,7 +441,7 @@ def run_ours(args):
         depth_host.copy_(depth, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(warmup):
         render(o_dev, d_dev)
     e2e_step()
     barrier(world)
@@ -311,39 +468,31 @@ def run_ours(args):
     barrier(world)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world)
     clocks = sampler.stop() if rank == 0 else None
+    reused = bool(out[2]["z_vals"].shape[1] == N_COARSE + N_IMPORTANCE and "rgb_coarse" in out[2] and
+                  os.environ.get("NERFW_REUSE_COARSE", "1") != "0")
+    evals_per_ray = (N_COARSE + N_IMPORTANCE) if reused else SAMPLES_PER_RAY
 
-    # ---- dominant kernel (fine-pass MLP) on its own, CUDA events on the launching stream -------------------------
+    # ---- the MLP launches of the step on their own, CUDA events on the launching stream --------------------------
     with torch.no_grad():
-        z_fine = out[2]["z_vals"].contiguous()
-        dn = ops.normalize_dirs(d_dev)
-        names, tensors = model.kernel_params()
-        pd = {n: t.detach() for n, t in zip(names, tensors)}
-        packed = model.packed_weights(names, tensors)
-        emb2 = emb_d.unsqueeze(0).contiguous()
-        roof = {}
+        z_all = out[2]["z_vals"].contiguous()
         z_coarse = out[2]["z_vals_coarse"].contiguous()
-        fine_mode = "fp16" if mode == "mixed" else mode          # kernel arithmetic of the fine pass (the dominant launch)
-        # (label, kernel mode, depths): the fine-pass launch of the headline mode, bf16 on the same shape, and -- for the
-        # mixed mode -- the bf16x3 coarse-pass launch
-        roof_runs = [(mode, fine_mode, z_fine), ("bf16", "bf16", z_fine)]
-        if mode == "mixed":
-            roof_runs.append(("coarse_bf16x3", "bf16x3", z_coarse))
-        for label, m, zz in roof_runs:
-            if label in roof:
-                continue
+        w_coarse = out[2]["weights_coarse"][..., 0].contiguous()
+        dn = ops.normalize_dirs(d_dev)
+        ws = model.kernel_state()[2]
+        packed = model.packed_weights()
+        emb2 = emb_d.unsqueeze(0).contiguous()
+        ur = torch.rand((n_rays, N_IMPORTANCE), device=dev, generator=gen)
+        _, z_new = ops.sample_pdf(z_coarse, w_coarse, N_IMPORTANCE, ur, want_zfine=True)
+        fine_mode = "fp16" if mode == "mixed" else mode
+        coarse_mode = "bf16x3" if mode == "mixed" else mode
+        # the launches a step performs (default: coarse pass on 64 depths with full outputs, fine pass on the 128 NEW
+        # depths); plus the 192-depth launch of the two-pass form and a bf16 launch of the same shape for comparison
+        runs = [("fine", fine_mode, z_new if reused else z_all, False), ("coarse", coarse_mode, z_coarse, False if reused else True),
+                ("two_pass_fine_192", fine_mode, z_all, False), ("bf16_192", "bf16", z_all, False)]
+        roof = {}
+        for label, m, zz, sig_only in runs:
             mid = nerfw.models.resolve_mode(m)
-            for _ in range(2):
-                raw_m = ops.mlp_fwd(pd, packed, o_dev, dn, zz, emb2, mid)
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = max(2, args.steps)
-            k0.record()
-            for _ in range(reps):
-                raw_m = ops.mlp_fwd(pd, packed, o_dev, dn, zz, emb2, mid)
-            k1.record()
-            torch.cuda.synchronize()
-            if zz is z_fine:
-                raw = raw_m
-            kms = k0.elapsed_time(k1) / reps
+            kms = timed(lambda: ops.mlp_fwd(ws, packed, o_dev, dn, zz, emb2, mid, sigma_only=sig_only), max(2, args.steps))
             flops = FLOP_PER_SAMPLE * float(zz.numel())
             ach = flops / (kms * 1e-3) / 1e12
             # tensor-pipe FLOPs actually issued: bf16x3 runs the trunk as 3 MMAs per product (the direction layer as one),
@@ -351,111 +500,128 @@ def run_ours(args):
             issued = ach * (3018496.0 if m == "bf16x3" else 1054464.0) / FLOP_PER_SAMPLE
             roof[label] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": ach / peaks["bf16_tflops_sustained"],
-                           # DRAM bytes per launch: 18.9 B/sample measured by ncu --set full on a 160k-ray crop
-                           # (profiles/r01_ncu_full_*.md: 141 MB read + 439 MB written for 30.7 M samples) x samples here
                            "traffic": 18.9 * float(zz.numel()),
-                           "kernel": ("mlp_tc_fwd_kernel<%s>" % {"bf16x3": "X3", "fp16": "F16", "bf16": "BF16"}[m]) if m != "fp32" else "mlp_ffma_fwd_kernel",
+                           "traffic_source": "constant: 18.9 B/sample from one ncu --set full capture (profiles/r01_ncu_full_mixed.md: "
+                                             "141 MB read + 439 MB written for 30.7 M samples), not re-measured per run",
+                           "kernel": ("mlp_tc_fwd_kernel<%s%s>" % ({"bf16x3": "X3", "fp16": "F16", "bf16": "BF16"}[m], ",SIGMA" if sig_only else ""))
+                           if m != "fp32" else "mlp_ffma_fwd_kernel",
                            "kernel_mode": m, "kernel_ms": kms, "samples_per_launch": int(zz.numel()),
+                           "algorithmic_flop_per_sample": FLOP_PER_SAMPLE,
                            "peak_source": f"bf16 dense sustained (fp16 and bf16 share the kind::f16 tensor-pipe rate), {peaks['source']}",
-                           "issued": issued, "issued_frac": issued / peaks["bf16_tflops_sustained"],
-                           "note": ("bf16x3 (fp32-parity split) issues 3 bf16 MMAs per trunk product, so the algorithmic frac is "
-                                    "bounded by ~0.35; issued_frac is the tensor-pipe rate against the same peak"
-                                    if m == "bf16x3" else
-                                    "fine pass of the mixed mode: single fp16 MMA per product; the coarse pass (1/4 of the samples) "
-                                    "runs in bf16x3, see roofline_other.mlp_coarse_bf16x3" if label == "mixed" else "")}
+                           "issued": issued, "issued_frac": issued / peaks["bf16_tflops_sustained"]}
+            if m == "bf16x3":
+                roof[label]["note"] = ("bf16x3 (fp32-parity split) issues 3 bf16 MMAs per trunk product, so the algorithmic frac is "
+                                       "bounded by ~0.35; issued_frac is the tensor-pipe rate against the same peak")
+        raw = ops.mlp_fwd(ws, packed, o_dev, dn, z_all, emb2, nerfw.models.resolve_mode(fine_mode))
         # HBM-bound kernels on the same frame
-        comp0, comp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ops.composite_fwd(raw, z_fine)
-        comp0.record()
-        for _ in range(5):
-            ops.composite_fwd(raw, z_fine)
-        comp1.record()
-        torch.cuda.synchronize()
-        cms = comp0.elapsed_time(comp1) / 5
-        cbytes = z_fine.numel() * 24.0 + n_rays * 20.0
-        zc = out[2]["z_vals_coarse"].contiguous()
-        wc = out[2]["weights_coarse"][..., 0].contiguous()
-        ur = torch.rand((n_rays, N_IMPORTANCE), device=dev)
-        ops.sample_pdf(zc, wc, N_IMPORTANCE, ur)
-        comp0.record()
-        for _ in range(5):
-            ops.sample_pdf(zc, wc, N_IMPORTANCE, ur)
-        comp1.record()
-        torch.cuda.synchronize()
-        rms = comp0.elapsed_time(comp1) / 5
+        cms = timed(lambda: ops.composite_fwd(raw, z_all), 5)
+        cbytes = z_all.numel() * 24.0 + n_rays * 20.0
+        rms = timed(lambda: ops.sample_pdf(z_coarse, w_coarse, N_IMPORTANCE, ur), 5)
         rbytes = n_rays * (3 * N_COARSE + 2 * N_IMPORTANCE) * 4.0
         g_rgb = torch.rand((n_rays, 3), device=dev)
         g_depth = torch.rand((n_rays, 1), device=dev)
-        ops.composite_bwd(raw, z_fine, g_rgb, g_depth, None, None)
-        comp0.record()
-        for _ in range(5):
-            ops.composite_bwd(raw, z_fine, g_rgb, g_depth, None, None)
-        comp1.record()
-        torch.cuda.synchronize()
-        bms = comp0.elapsed_time(comp1) / 5
-        bbytes = z_fine.numel() * 40.0
-        hbm = {"composite_fwd": {"bound": "hbm", "achieved": cbytes / (cms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                                 "unit": "GB/s", "frac": cbytes / (cms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": cms},
-               "composite_bwd": {"bound": "hbm", "achieved": bbytes / (bms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                                 "unit": "GB/s", "frac": bbytes / (bms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": bms},
-               "sample_pdf": {"bound": "hbm", "achieved": rbytes / (rms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                              "unit": "GB/s", "frac": rbytes / (rms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": rms}}
+        bms = timed(lambda: ops.composite_bwd(raw, z_all, g_rgb, g_depth, None, None), 5)
+        bbytes = z_all.numel() * 40.0
 
-    # ---- secondary numbers: the other tensor-core mode, and the training step (BASELINE.json configs[2]) ------------
+        def hb(nbytes, ms, **extra):
+            return {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": ms, **extra}
+        hbm = {"composite_fwd": hb(cbytes, cms), "composite_bwd": hb(bbytes, bms), "sample_pdf": hb(rbytes, rms)}
+        if reused:
+            raw_c = ops.mlp_fwd(ws, packed, o_dev, dn, z_coarse, emb2, nerfw.models.resolve_mode(coarse_mode))
+            raw_f = ops.mlp_fwd(ws, packed, o_dev, dn, z_new, emb2, nerfw.models.resolve_mode(fine_mode))
+            mms = timed(lambda: ops.merge_raw(z_coarse, raw_c, z_new, raw_f), 5)
+            # per ray: read z_c, z_f (4 B) and both raw records (16 B) per sample, write the merged records (16 B)
+            hbm["merge_raw"] = hb(n_rays * (N_COARSE + N_IMPORTANCE) * 36.0, mms)
+            del raw_c, raw_f
+        # BASELINE.json configs[4]: 4096 rays, 256 + 512 samples, bf16 MLP -- whole call, and its resampling kernel alone
+        o5, d5 = o_dev[:4096].contiguous(), d_dev[:4096].contiguous()
+        s_ms = timed(lambda: nerfw.volume_render(model, o5, d5, NEAR, FAR, 256, 512, appearance_embedding=emb_d, perturb=False,
+                                                 mlp_dtype="bf16", generator=gen), 5)
+        ex5 = nerfw.volume_render(model, o5, d5, NEAR, FAR, 256, 512, appearance_embedding=emb_d, perturb=False, mlp_dtype="bf16",
+                                  generator=gen)[2]
+        b5 = 65536                                        # the kernel alone on enough rays to fill the machine
+        z5 = ex5["z_vals_coarse"].repeat(b5 // 4096, 1).contiguous()
+        w5 = ex5["weights_coarse"][..., 0].repeat(b5 // 4096, 1).contiguous()
+        u5 = torch.rand((b5, 512), device=dev, generator=gen)
+        p_ms = timed(lambda: ops.sample_pdf(z5, w5, 512, u5), 5)
+        stress = {"ms_per_call": s_ms, "value": 4096 / (s_ms * 1e-3) / 1e6, "unit": "Mrays/s", "rays": 4096, "samples": "256+512",
+                  "mlp_mode": "bf16", "mlp_evals_per_ray": 768 if reused else 1024,
+                  "tflops_algorithmic": FLOP_PER_SAMPLE * 4096.0 * (768 if reused else 1024) / (s_ms * 1e-3) / 1e12,
+                  "sample_pdf_256_512": hb(b5 * (3 * 256 + 2 * 512) * 4.0, p_ms, rays=b5, kernel="sample_pdf_kernel<256,512>")}
+        del z5, w5, u5, raw
+
+    # ---- secondary numbers ------------------------------------------------------------------------------------------
     other_modes = {}
-    for m in ("bf16", "bf16x3", "mixed"):
-        if m == mode:
-            continue
-        with torch.no_grad():
-            nerfw.volume_render(model, o_dev, d_dev, NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb_d,
-                                perturb=False, mlp_dtype=m, generator=gen)
-            barrier(world)
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for _ in range(2):
-                nerfw.volume_render(model, o_dev, d_dev, NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb_d,
-                                    perturb=False, mlp_dtype=m, generator=gen)
-            a1.record()
-            barrier(world)
-        ms = max_over_ranks(a0.elapsed_time(a1) / 2, world)
-        other_modes[m] = {"value": world * n_rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms}
-    # opt-in: one network for both passes -> the fine pass evaluates only the 128 new samples (192 MLP evaluations per ray)
-    with torch.no_grad():
-        nerfw.volume_render(model, o_dev, d_dev, NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb_d,
-                            perturb=False, mlp_dtype=mode, generator=gen, reuse_coarse=True)
+
+    def frame_time(label, reps=2, **kw):
+        ms = timed(lambda: render(o_dev, d_dev, **kw), reps, world)
+        other_modes[label] = {"value": world * n_rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms, **{k: str(v) for k, v in kw.items()}}
+
+    frame_time("two_pass_no_reuse", reuse_coarse=False)          # 64 + 192 = 256 MLP evaluations per ray (round-1 headline form)
+    other_modes["two_pass_no_reuse"]["mlp_evals_per_ray"] = SAMPLES_PER_RAY
+    for m in ("bf16x3", "bf16", "mixed"):
+        if m != mode:
+            frame_time(f"mode_{m}", mlp_dtype=m)
+    if not args.quick:
+        render(o_dev[:4096], d_dev[:4096], mlp_dtype="fp32")      # warm (first launch of the CUDA-core kernels)
         barrier(world)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(2):
-            nerfw.volume_render(model, o_dev, d_dev, NEAR, FAR, N_COARSE, N_IMPORTANCE, appearance_embedding=emb_d,
-                                perturb=False, mlp_dtype=mode, generator=gen, reuse_coarse=True)
-        a1.record()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        render(o_dev, d_dev, mlp_dtype="fp32")                    # the only all-fp32-arithmetic mode (CUDA cores): one frame
+        f1.record()
         barrier(world)
-    ms = max_over_ranks(a0.elapsed_time(a1) / 2, world)
-    other_modes["reuse_coarse_opt_in"] = {"value": world * n_rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms,
-                                          "mlp_mode": mode, "mlp_evals_per_ray": N_COARSE + N_IMPORTANCE,
-                                          "note": "not the headline: the coarse samples are not re-evaluated in the fine pass"}
+        ms32 = max_over_ranks(f0.elapsed_time(f1), world)
+        other_modes["mode_fp32"] = {"value": world * n_rays / (ms32 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms32, "mlp_dtype": "fp32"}
     # the reference's own calling pattern: 4096-ray chunks with a device->host copy per chunk
     # (render_aligned_spiral.py:136-155), one frame
     with torch.no_grad():
+        for j in range(0, 3 * 4096, 4096):
+            render(o_dev[j:j + 4096], d_dev[j:j + 4096])
         barrier(world)
         t0 = time.perf_counter()
         parts = []
         for j in range(0, n_rays, 4096):
-            c_rgb, c_depth, _ = nerfw.volume_render(model, o_dev[j:j + 4096], d_dev[j:j + 4096], NEAR, FAR, N_COARSE,
-                                                    N_IMPORTANCE, appearance_embedding=emb_d, perturb=False,
-                                                    mlp_dtype=mode, generator=gen)
+            c_rgb, c_depth, _ = render(o_dev[j:j + 4096], d_dev[j:j + 4096])
             parts.append((c_rgb.cpu(), c_depth.cpu()))
         barrier(world)
         chunk_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world)
+        # host time of one call (no sync inside): what the shim adds per chunk on top of the kernels
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            render(o_dev[:4096], d_dev[:4096])
+        host_us = (time.perf_counter() - t0) / 50 * 1e6
+        torch.cuda.synchronize()
     other_modes["chunked_4096_with_cpu_copy"] = {"value": world * n_rays / (chunk_ms * 1e-3) / 1e6, "unit": "Mrays/s",
                                                  "ms_per_step": chunk_ms, "mlp_mode": mode,
-                                                 "calls_per_frame": (n_rays + 4095) // 4096}
+                                                 "calls_per_frame": (n_rays + 4095) // 4096,
+                                                 "host_us_per_call_enqueue": host_us}
     train = bench_train_step(nerfw, sd, dev, world, mode)
     if mode != "bf16x3":
         train["bf16x3_forward_ms_per_step"] = bench_train_step(nerfw, sd, dev, world, "bf16x3")["ms_per_step"]
     if mode != "bf16":
         train["bf16_forward_ms_per_step"] = bench_train_step(nerfw, sd, dev, world, "bf16")["ms_per_step"]
+    train["per_ray_embeddings_ms_per_step"] = bench_train_step(nerfw, sd, dev, world, mode, per_ray_emb=True)["ms_per_step"]
+
+    legs = {}
+    if world > 1:
+        try:
+            legs["dp_check"] = dp_check(nerfw, sd, dev, rank, world)
+        except Exception as e:  # noqa: BLE001  (a failed secondary leg must not lose the headline line)
+            legs["dp_check"] = {"error": repr(e)[:300]}
+    if not args.quick:
+        try:
+            ro0, rd0 = nerfw.get_rays(H, W, focal, torch.from_numpy(poses[0]).to(dev))   # the SAME frame on every rank
+            legs["strong_one_frame"] = strong_leg(nerfw, model, emb_d, dev, rank, world, mode, ro0.reshape(-1, 3).contiguous(),
+                                                  rd0.reshape(-1, 3).contiguous())
+        except Exception as e:  # noqa: BLE001
+            legs["strong_one_frame"] = {"error": repr(e)[:300]}
+        if args.spiral_frames > 0:
+            try:
+                legs["spiral_120"] = spiral_leg(nerfw, model, emb_d, dev, rank, world, mode, args.spiral_frames)
+            except Exception as e:  # noqa: BLE001
+                legs["spiral_120"] = {"error": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -463,41 +629,90 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # ---- secondary baseline: the reference algorithm in PyTorch eager on the B200 ------------------------
+    eager = None
+    if not args.quick:
+        try:
+            import nerfw_oracle as orc
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            sd_gpu = {k: v.to(dev) for k, v in sd.items()}
+            oe, de = o_dev[320000:324096].contiguous(), d_dev[320000:324096].contiguous()
+            ue = torch.rand(4096, N_IMPORTANCE, device=dev)
+            with torch.no_grad():
+                e_ms = timed(lambda: orc.render_hier(sd_gpu, sd_gpu, oe, de, NEAR, FAR, N_COARSE, N_IMPORTANCE, emb=emb_d, perturb=False, u_rand=ue), 3)
+                o_ms = timed(lambda: render(oe, de, u_rand=ue), 10)
+            eager = {"value": 4096 / (e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_4096_rays": e_ms, "ours_ms_per_4096_rays": o_ms,
+                     "kind": "reference algorithm (oracle restatement) in torch eager on this GPU, fp32 cuBLAS, TF32 off, 4096-ray call"}
+        except Exception as e:  # noqa: BLE001
+            eager = {"error": repr(e)[:300]}
+
     # ---- CPU baseline on a bounded sample + parity of the same sample ----------------------------------------------
     cpu = None
     parity = None
     if not args.no_cpu_baseline:
-        n_cpu, dt, cores, (oc, dc, u, rgb_o, depth_o, acc_o) = cpu_sample(sd, emb, args.cpu_rays, poses[0])
-        with torch.no_grad():
-            rgb_g, depth_g, ex_g = nerfw.volume_render(model, oc.to(dev), dc.to(dev), NEAR, FAR, N_COARSE, N_IMPORTANCE,
-                                                       appearance_embedding=emb_d, perturb=False, mlp_dtype=mode, u_rand=u)
-        parity = {"rays": n_cpu, "rgb_max_abs": float((rgb_g.cpu() - rgb_o).abs().max()),
+        # every k-th ray of the WHOLE frame (borders included), random-init weights: timed as the CPU baseline
+        n_cpu, dt, cores, (oc, dc, u, rgb_o, depth_o, acc_o) = cpu_sample(sd, emb, args.cpu_rays, poses[0], strided=True)
+        rgb_g, depth_g, ex_g = render(oc.to(dev), dc.to(dev), u_rand=u)
+        parity = {"rays": n_cpu, "sample": "every k-th ray of the whole 800x800 frame", "mode": mode, "reuse_coarse": reused,
+                  "rgb_max_abs": float((rgb_g.cpu() - rgb_o).abs().max()),
                   "depth_max_abs": float((depth_g.cpu() - depth_o).abs().max()),
-                  "acc_max_abs": float((ex_g["acc"].cpu() - acc_o).abs().max())}
+                  "acc_max_abs": float((ex_g["acc"].cpu() - acc_o).abs().max()),
+                  "rgb": parity_stats(rgb_g, rgb_o), "depth": parity_stats(depth_g, depth_o), "acc": parity_stats(ex_g["acc"], acc_o)}
         cpu = {"value": n_cpu / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} rays (centre rows of the same 800x800 view), coarse 64 + fine 192, one pass, {dt:.1f} s"}
+               "sample": f"{n_cpu} rays (every k-th ray of the same 800x800 view), coarse 64 + fine 192, one pass, {dt:.1f} s"}
+        # the same on the DENSE variant (density head x200, bias +1: mean acc ~ 1, an opaque scene), a third of the rays
+        sd_dense = {k: v.clone() for k, v in sd.items()}
+        sd_dense["density_head.weight"] *= 200.0
+        sd_dense["density_head.bias"] += 1.0
+        n_d, _, _, (od, dd, ud, rgb_od, depth_od, acc_od) = cpu_sample(sd_dense, emb, max(2400, args.cpu_rays // 3), poses[0], strided=True)
+        m_dense = nerfw.NeRF(Config())
+        m_dense.load_state_dict(sd_dense, strict=True)
+        m_dense = m_dense.to(dev).eval()
+        with torch.no_grad():
+            rgb_d, depth_d, ex_d = nerfw.volume_render(m_dense, od.to(dev), dd.to(dev), NEAR, FAR, N_COARSE, N_IMPORTANCE,
+                                                       appearance_embedding=emb_d, perturb=False, mlp_dtype=mode, u_rand=ud)
+            _, depth_d32, _ = nerfw.volume_render(m_dense, od.to(dev), dd.to(dev), NEAR, FAR, N_COARSE, N_IMPORTANCE,
+                                                  appearance_embedding=emb_d, perturb=False, mlp_dtype="fp32", u_rand=ud)
+        parity["dense"] = {"rays": n_d, "mean_acc": float(acc_od.mean()), "rgb": parity_stats(rgb_d, rgb_od),
+                           "depth": parity_stats(depth_d, depth_od), "acc": parity_stats(ex_d["acc"], acc_od),
+                           "depth_fp32_kernel": parity_stats(depth_d32, depth_od),
+                           "note": "rays over the bar are resampling discontinuities of the reference algorithm itself (the denom < 1e-5 "
+                                   "branch of src/ray_utils.py:136-137 and searchsorted ties flip on last-bit differences of the coarse "
+                                   "weights): the all-fp32 CUDA-core kernel (depth_fp32_kernel) shows the same tail"}
 
     value = world * n_rays * args.steps / (ms_total * 1e-3) / 1e6
     e2e_val = world * n_rays * args.steps / (e2e_ms * 1e-3) / 1e6
+    dominant = max(("fine", "coarse"), key=lambda k: roof[k]["kernel_ms"])
+    roof[dominant]["share_of_step"] = roof[dominant]["kernel_ms"] / (ms_total / args.steps)
     line = {
-        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"mixed": "bf16x3 coarse pass + fp16 fine pass (tcgen05 kind::f16, fp32 accumulate; fp32 parity bars)",
                   "bf16x3": "bf16x3 (fp32-parity split, fp32 accumulate)", "bf16": "bf16", "fp16": "fp16", "fp32": "f32"}[mode],
         "data": "synthetic",
         "config": {"workload": "800x800 view render, 64+128 samples, random-init NeRF-W (BASELINE.json configs[1])",
-                   "rays_per_step_per_gpu": n_rays, "mlp_evals_per_ray": SAMPLES_PER_RAY, "mlp_mode": mode,
+                   "rays_per_step_per_gpu": n_rays, "mlp_evals_per_ray": evals_per_ray, "mlp_mode": mode,
+                   "reuse_coarse": reused,
+                   "evals_note": ("one network for both passes (the reference's only case, src/train.py:30): the fine pass evaluates the 128 "
+                                  "new depths and re-uses the coarse pass's records at the 64 coarse depths -> 192 evaluations per ray; the "
+                                  "two-pass form (256 evaluations, round-1 headline) is other_modes.two_pass_no_reuse") if reused else
+                                 "two-pass form: 64 coarse + 192 fine evaluations per ray",
                    "call": "one whole-frame volume_render per step", "parallelism": f"rays/frames sharded x{world}, no collective",
+                   "warmup_requested": args.warmup,
                    "l2": "per-step working set 2.6 GB of sample buffers >> 126 MB L2 (inputs larger than L2)"},
         "e2e": {"value": e2e_val, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(o_host.numel() * 4 + d_host.numel() * 4),
                 "d2h_bytes_per_step": int(rgb_host.numel() * 4 + depth_host.numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": roof[mode],
-        "roofline_other": {**{f"mlp_{k}": v for k, v in roof.items() if k != mode}, **hbm},
+        "roofline": {**roof[dominant], "launch": dominant + " pass"},
+        "roofline_other": {**{f"mlp_{k}": v for k, v in roof.items() if k != dominant}, **hbm},
         "other_modes": other_modes,
         "train_step": train,
+        "stress_256_512": stress,
+        "eager_baseline": eager,
+        **legs,
         "cpu_baseline": cpu,
         "parity_vs_oracle": parity,
     }

@@ -355,6 +355,8 @@ extern "C" int nerfw_merge_raw(const float* z_coarse, const float* raw_coarse, c
   NERFW_REQUIRE(z_coarse && raw_coarse && z_fine && raw_fine && raw_out, "nerfw_merge_raw: null pointer");
   NERFW_REQUIRE(aligned16(raw_coarse) && aligned16(raw_fine) && aligned16(raw_out), "nerfw_merge_raw: raw buffers must be 16-byte aligned");
   const size_t smem = (size_t)MG_WARPS * (n_samples + n_importance) * sizeof(float);
+  if (smem > 48 * 1024)   // up to 64 KB at N + NI = 4096
+    NERFW_CUDA(cudaFuncSetAttribute(merge_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = ceil_div64(n_rays, MG_WARPS);
   const int64_t cap = (int64_t)sm_count() * 32;
   if (blocks > cap) blocks = cap;

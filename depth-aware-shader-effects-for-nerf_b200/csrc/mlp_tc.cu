@@ -489,418 +489,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// X3: split (three-MMA) arithmetic; F16 (with X3 = false): operands in fp16 instead of bf16 (11-bit significand, activations
-// saturate at 65504) from the fp16 weight image at packed + f16_offset.
-// PAIR: two CTAs of a cluster work on two consecutive sample tiles with ONE tcgen05.mma.cta_group::2 chain (M = 256)
-// issued by the leader CTA.  B is split by N over the pair, so every SM streams, stores and reads only HALF of each
-// weight chunk (16 KB stages, twice as many of them): the shared-memory bandwidth of the weight path -- what bounds the
-// single-pass modes -- is halved.  Peer-CTA epilogue warps signal the leader's mbarriers through the cluster; the MMA
-// completions are multicast to both CTAs.
-template <bool X3, bool F16 = false>
-__global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_pair_kernel(const uint8_t* __restrict__ packed, SampleSource src,
-                                                                 const float4* __restrict__ app_off, int64_t n_total,
-                                                                 float4* __restrict__ raw, uint32_t* __restrict__ masks, int flags,
-                                                                 long long* __restrict__ timeline, size_t f16_offset) {
-  static_assert(!(X3 && F16), "the fp16 mode is single pass");
-  constexpr bool PAIR = true, SIGMA = false;
-  // flags: 1 = profiling, reuse whatever the ring holds after the first tile (wrong results).  SIGMA (sigma only): the
-  // direction layer and the rgb head are skipped and raw = (0, 0, 0, sigma) -- all the coarse pass of a hierarchical
-  // inference render needs (its weights place the fine samples; its colour is never looked at)
-  const int debug_skip_weights = flags & 1;
-  constexpr bool sigma_only = SIGMA;   // compile time: the common path carries none of its branches
-  constexpr int n_chunks = sigma_only ? N_BIG : N_CHUNKS;
-  extern __shared__ uint8_t smem_dyn[];
-  uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + SM_BAR);
-  // bf16 mode has no lo operand tiles: that space is a fifth ring stage (deeper weight prefetch across the epilogue gaps)
-  constexpr uint32_t STAGE_BYTES = PAIR ? BIG_CHUNK / 2 : BIG_CHUNK;
-  constexpr int STAGES = (X3 ? NSTAGES : NSTAGES + 1) * (PAIR ? 2 : 1);
-  constexpr uint32_t RING = X3 ? SM_RING : SM_RING - BIG_CHUNK;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
-  constexpr uint32_t PED_HI = X3 ? SM_PED_HI : SM_PEX_LO;
-  struct RingPipe {
-    int stage = 0;
-    uint32_t phase = 0;
-    __device__ __forceinline__ void advance() {
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
-  };
-  uint64_t* empty = full + STAGES;
-  uint64_t* pfull = empty + STAGES;                    // PAIR, leader: the peer CTA's half of the stage has landed
-  uint64_t* acc_full = pfull + (PAIR ? STAGES : 0);
-  // per-K-block operand barriers, accumulator-free and encodings-ready barriers (one arrival per epilogue warp)
-  uint64_t* a_kb = acc_full + 2;
-  uint64_t* acc_free = a_kb + 4;
-  uint64_t* pe_ready = acc_free + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM_TMEMPTR);
-  float* vec = reinterpret_cast<float*>(sm + SM_VEC);
-  float* sig_part = reinterpret_cast<float*>(sm + SM_SIG);
-  float4* rgb_part = reinterpret_cast<float4*>(sm + SM_RGB);
-
-  if (warp == F_PRODUCER_WARP && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    if (PAIR) for (int i = 0; i < STAGES; ++i) mbar_init(&pfull[i], 1);
-    mbar_init(acc_full, 1);
-    constexpr int EPI_ARRIVALS = F_EPI_WARPS * (PAIR ? 2 : 1);   // the peer CTA's epilogue warps arrive here too
-    for (int i = 0; i < 4; ++i) mbar_init(&a_kb[i], EPI_ARRIVALS);
-    mbar_init(acc_free, EPI_ARRIVALS);
-    mbar_init(pe_ready, EPI_ARRIVALS);
-    fence_mbar_init();
-  }
-  if (warp == F_MMA_WARP) {
-    if (PAIR) tmem_alloc_2cta<512>(tmem_ptr); else tmem_alloc<512>(tmem_ptr);
-  }
-  if (warp < F_EPI_WARPS) {
-    const float* gv = reinterpret_cast<const float*>(packed + W_BYTES);
-    for (int i = tid; i < V_FLOATS; i += F_EPI_THREADS) vec[i] = __ldg(gv + i);
-  }
-  tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const int64_t ntiles = (n_total + TM - 1) / TM;
-  // tile loop of every role: `base` is the (first) tile of this CTA (pair); a pair's second tile may lie past the end
-  const int64_t tile0 = PAIR ? 2 * (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
-  const int64_t tstride = PAIR ? (int64_t)(gridDim.x & ~1u) : (int64_t)gridDim.x;
-  const int64_t stamp_tile = blockIdx.x == 0 ? 2 * tstride : -1;   // profiling: the tile whose events are stamped (CTA 0, third tile)
-  // arrival on a leader-side barrier from either CTA
-  auto arrive_leader = [&](uint64_t* bar) {
-    if constexpr (PAIR) {
-      __syncwarp();
-      if (lane == 0) {
-        if (rank != 0) mbar_arrive_cluster(map_to_cta(smem_u32(bar), 0));
-        else mbar_arrive(bar);
-      }
-    } else {
-      mbar_arrive_warp(bar);
-    }
-  };
-  // Split (3-MMA) arithmetic for the direction layer only in training mode: its ReLU gates then match the fp32 forward.
-  // For inference the layer runs as a single bf16 MMA -- it only feeds the rgb sigmoid (sigma, hence depth, acc and the
-  // resampling, come from the trunk); measured effect on rendered rgb <= 5e-5.
-  const bool dir_split = X3 && masks != nullptr;
-
-  if (warp == F_PRODUCER_WARP) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
-      RingPipe p;
-      for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
-        size_t off = 0;
-        for (int i = 0; i < n_chunks; ++i) {
-          const uint32_t sz = i < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
-          const uint32_t part = PAIR ? sz / 2 : sz;   // this CTA's rows of the chunk (B is split by N over the pair)
-          const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
-          for (int v = 0; v < copies; ++v) {
-            mbar_wait(&empty[p.stage], p.phase ^ 1);
-            if (debug_skip_weights && tile != tile0) {
-              mbar_arrive(&full[p.stage]);   // profiling only: reuse whatever the stage holds (results are wrong)
-            } else {
-              mbar_arrive_expect_tx(&full[p.stage], part);
-              const uint8_t* srcw = (F16 ? packed + f16_offset + chunk_offset_f16(i) : packed + off + (size_t)v * sz) + (size_t)rank * part;
-              bulk_g2s(sm + RING + p.stage * STAGE_BYTES, srcw, part, &full[p.stage]);
-            }
-            p.advance();
-          }
-          off += 2ull * sz;
-        }
-      }
-    }
-  } else if (warp == F_MMA_WARP) {
-    // ===================== MMA issuer =====================
-    if (PAIR && rank != 0) {
-      // peer CTA: this thread only relays "my half of ring stage s has landed" to the leader, in consumption order
-      if (lane == 0) {
-        RingPipe p;
-        for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
-          for (int i = 0; i < n_chunks; ++i) {
-            const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
-            for (int v = 0; v < copies; ++v) {
-              mbar_wait(&full[p.stage], p.phase);
-              mbar_arrive_cluster(map_to_cta(smem_u32(&pfull[p.stage]), 0));
-              p.advance();
-            }
-          }
-        }
-      }
-    } else
-    if (lane == 0) {
-      RingPipe p;
-      constexpr uint32_t MM = PAIR ? 256 : 128;   // rows per MMA: both CTAs' tiles
-      const uint32_t idesc256 = F16 ? idesc_f16(MM, 256) : idesc_bf16(MM, 256);
-      const uint32_t idesc128 = F16 ? idesc_f16(MM, 128) : idesc_bf16(MM, 128);
-      const uint32_t ring = smem_u32(sm + RING);
-      const uint32_t d_acc = tmem + COL_ACC;
-      // one 64-wide K block: A (hi[,lo]) x W chunk (hi[,lo]); a_* are either TMEM addresses (TS) or smem descs (SS)
-      auto kblock = [&](bool from_tmem, uint64_t a_hi, uint64_t a_lo, uint32_t idesc, int ksteps, bool first, bool split = X3) {
-        mbar_wait(&full[p.stage], p.phase);
-        mbar_wait(&pfull[p.stage], p.phase);   // the peer CTA's half (relayed)
-        tc_fence_after();
-        uint64_t b = smem_desc_sw128(ring + p.stage * STAGE_BYTES);
-        for (int k = 0; k < ksteps; ++k) {
-          uint32_t accf = (first && k == 0) ? 0u : 1u;
-          if (from_tmem) mma_ts_2cta(d_acc, (uint32_t)a_hi + 8 * k, b + 2 * k, idesc, accf);
-          else mma_ss_2cta(d_acc, a_hi + 2 * k, b + 2 * k, idesc, accf);
-        }
-        if (split) {
-          for (int k = 0; k < ksteps; ++k) {
-            if (from_tmem) mma_ts_2cta(d_acc, (uint32_t)a_lo + 8 * k, b + 2 * k, idesc, 1u);
-            else mma_ss_2cta(d_acc, a_lo + 2 * k, b + 2 * k, idesc, 1u);
-          }
-        }
-        mma_commit_2cta(&empty[p.stage]);
-        p.advance();
-        if (split) {
-          mbar_wait(&full[p.stage], p.phase);
-        mbar_wait(&pfull[p.stage], p.phase);   // the peer CTA's half (relayed)
-        tc_fence_after();
-          uint64_t bl = smem_desc_sw128(ring + p.stage * STAGE_BYTES);
-          for (int k = 0; k < ksteps; ++k) {
-            if (from_tmem) mma_ts_2cta(d_acc, (uint32_t)a_hi + 8 * k, bl + 2 * k, idesc, 1u);
-            else mma_ss_2cta(d_acc, a_hi + 2 * k, bl + 2 * k, idesc, 1u);
-          }
-          mma_commit_2cta(&empty[p.stage]);
-          p.advance();
-        }
-      };
-      const uint64_t pex_hi = smem_desc_sw128(smem_u32(sm + SM_PEX_HI)), pex_lo = smem_desc_sw128(smem_u32(sm + SM_PEX_LO));
-      const uint64_t ped_hi = smem_desc_sw128(smem_u32(sm + PED_HI)), ped_lo = smem_desc_sw128(smem_u32(sm + SM_PED_LO));
-      // The epilogue frees the accumulator as soon as it sits in registers and publishes the next A operand one 64-wide
-      // K block at a time, so the MMAs of layer l+1 start while most of epilogue l is still running.
-      uint32_t ph_free = 0, ph_pe = 0, ph_kb = 0;
-      auto wait_bar = [&](uint64_t* bar, uint32_t phase) {
-        mbar_wait(bar, phase);   // (PAIR: arrivals also come from the peer CTA, with release.cluster)
-        tc_fence_after();
-      };
-      for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
-        wait_bar(pe_ready, ph_pe);
-        ph_pe ^= 1;
-        NERFW_STAMP(0);
-        for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
-          wait_bar(acc_free, ph_free);
-          ph_free ^= 1;
-          NERFW_STAMP(10 + layer * 8);       // accumulator free seen by the MMA thread
-          if (layer == 0) {
-            kblock(false, pex_hi, pex_lo, idesc256, 4, true);
-          } else {
-            for (int kb = 0; kb < 4; ++kb) {
-              wait_bar(&a_kb[kb], ph_kb);
-              if (kb == 0) NERFW_STAMP(11 + layer * 8);   // first operand K block seen
-              if (kb == 3) NERFW_STAMP(12 + layer * 8);   // last operand K block seen
-              kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc256, 4, kb == 0);
-            }
-            ph_kb ^= 1;
-            if (layer == NERFW_SKIP) kblock(false, pex_hi, pex_lo, idesc256, 4, false);
-          }
-          mma_commit_2cta(acc_full);
-          NERFW_STAMP(13 + layer * 8);       // all MMAs of the layer issued
-        }
-        if (sigma_only) continue;
-        wait_bar(acc_free, ph_free);
-        ph_free ^= 1;
-        for (int kb = 0; kb < 4; ++kb) {
-          wait_bar(&a_kb[kb], ph_kb);
-          kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, kb == 0, dir_split);
-        }
-        ph_kb ^= 1;
-        kblock(false, ped_hi, ped_lo, idesc128, 2, false, dir_split);
-        mma_commit_2cta(acc_full);
-      }
-    }
-  } else {
-    // ===================== encoders + epilogues (16 warps, thread <-> sample row x column quarter) ==========
-    const uint32_t quad = warp & 3, cq = warp >> 2;
-    const uint32_t row = quad * 32 + lane;
-    const uint32_t tlane = tmem + ((quad * 32) << 16);
-    uint32_t acc_phase = 0;
-    uint8_t* pex_hi = sm + SM_PEX_HI;
-    uint8_t* pex_lo = sm + SM_PEX_LO;
-    uint8_t* ped_hi = sm + PED_HI;
-    arrive_leader(acc_free);   // the accumulator starts out free
-    // ---- encodings (src/models.py:35-44).  Column quarters 0 / 1 write position features 0..31 / 32..63 of a tile,
-    // quarter 2 its direction tile.  They are not on the MMA critical path: the position tile of the NEXT sample tile and
-    // the direction tile of the current one are filled in between two trunk epilogues, once the skip layer has consumed
-    // the position tile, while the tensor pipe works on layer 6.
-    auto encode_pos = [&](int64_t t) {
-      if (cq < 2) {
-        const int64_t sr = t * TM + row;
-        float x[3] = {0.f, 0.f, 0.f};
-        if (sr < n_total) src.position(sr, x);
-        float v[32];
-        if (cq == 0) {
-          pos_features32<0, !X3>(x, v);
-          store_features32<X3, F16>(pex_hi, pex_lo, row, 0, v);
-        } else {
-          pos_features32<1, !X3>(x, v);
-          store_features32<X3, F16>(pex_hi, pex_lo, row, 32, v);
-        }
-      }
-      fence_proxy_async_smem();
-      arrive_leader(pe_ready);
-    };
-    auto encode_dir = [&](int64_t t) {
-      if (cq == 2) {
-        const int64_t sr = t * TM + row;
-        float d[3] = {0.f, 0.f, 0.f};
-        if (sr < n_total) src.direction(sr, d);
-        float v[32];
-        dir_features32<!X3>(d, v);
-        if (dir_split) store_features32<true>(ped_hi, sm + SM_PED_LO, row, 0, v);
-        else store_features32<false, F16>(ped_hi, ped_hi, row, 0, v);
-        fence_proxy_async_smem();   // ordered before this warp's later a_kb arrivals, which the MMA thread waits on
-      }
-    };
-    if (tile0 < ntiles) encode_pos(tile0 + rank);
-    for (int64_t base = tile0; base < ntiles; base += tstride) {
-      const int64_t tile = base + rank;   // a pair's second tile may lie past the end: all its rows are dead
-      const int64_t s = tile * TM + row;
-      const bool live = s < n_total;
-      // ---- trunk epilogues: acc -> bias, ReLU -> bf16 (hi[,lo]) -> next layer's A operand in TMEM ----
-      float sig = 0.f;
-      // Thread <-> (row, accumulator columns 64 cq .. 64 cq + 63).  All 64 values are pulled into registers first and the
-      // accumulator is released; the four 16-column granules are then finished and published one at a time -- granule
-      // kb of the four column quarters is K block kb of the next layer (K order: kperm_feature in mlp_tc_layout.cuh) --
-      // so the next layer's MMAs overlap with three quarters of this epilogue.
-      for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
-        mbar_wait(acc_full, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (tid == 0) NERFW_STAMP(14 + layer * 8);   // accumulator complete seen by the epilogue
-        const float* bias = vec + V_PTSB + layer * 256;
-        // inference: the direction layer consumes A_hi only
-        const bool want_lo = X3 && (layer != NERFW_LAYERS - 1 || dir_split);
-        uint32_t r[4][16];
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) tmem_ld16(tlane + COL_ACC + cq * 64 + kb * 16, r[kb]);
-        tmem_wait_ld();
-        tc_fence_before();
-        arrive_leader(acc_free);
-        if (tid == 0) NERFW_STAMP(15 + layer * 8);   // accumulator in registers
-        if (sigma_only && layer == NERFW_LAYERS - 1) {
-          // nobody consumes layer 7's activations as an operand: only the density head's dot product
-#pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            const uint32_t col = cq * 64 + kb * 16;
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              sig = fmaf(fmaxf(__fadd_rn(__uint_as_float(r[kb][e]), bias[col + e]), 0.f), vec[V_DENW + col + e], sig);
-          }
-          continue;
-        }
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint32_t col = cq * 64 + kb * 16;         // accumulator column = output feature
-          const uint32_t apos = (kb * 64 + cq * 16) >> 1;  // operand position: granule kb of quarter cq (kperm_feature)
-          const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-          uint32_t ph[8];
-          float a[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 bb = b4[j4];
-            unpack2f(add2(pack2(r[kb][4 * j4], r[kb][4 * j4 + 1]), pack2f(bb.x, bb.y)), a[4 * j4], a[4 * j4 + 1]);
-            unpack2f(add2(pack2(r[kb][4 * j4 + 2], r[kb][4 * j4 + 3]), pack2f(bb.z, bb.w)), a[4 * j4 + 2], a[4 * j4 + 3]);
-            ph[2 * j4] = F16 ? relu_pack_f16x2(a[4 * j4], a[4 * j4 + 1]) : relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
-            ph[2 * j4 + 1] = F16 ? relu_pack_f16x2(a[4 * j4 + 2], a[4 * j4 + 3]) : relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
-          }
-          tmem_st8(tlane + COL_AHI + apos, ph);
-          if (want_lo) {  // lo = bf16(relu(a) - hi)
-            uint32_t pl[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float l0v, l1v;
-              unpack2f(sub2(pack2f(fmaxf(a[2 * j], 0.f), fmaxf(a[2 * j + 1], 0.f)), pack2(ph[j] << 16, ph[j] & 0xffff0000u)), l0v, l1v);
-              pl[j] = pack_bf16x2(l0v, l1v);
-            }
-            tmem_st8(tlane + COL_ALO + apos, pl);
-          }
-          if (masks && (!PAIR || tile < ntiles)) {  // 16 ReLU gates of this slice (PAIR: not for the dead tile of an odd tail) = one half of gate word col / 32
-            uint32_t bits = 0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) bits |= (a[j] > 0.f ? 1u : 0u) << j;
-            reinterpret_cast<unsigned short*>(masks)[2 * mask_index(tile, layer, row, 0, (int)(col >> 5)) + ((col >> 4) & 1)] = (unsigned short)bits;
-          }
-          if (layer == NERFW_LAYERS - 1) {
-            const float4* w4 = reinterpret_cast<const float4*>(vec + V_DENW + col);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 ww = w4[j4];
-              sig = fmaf(fmaxf(a[4 * j4], 0.f), ww.x, sig); sig = fmaf(fmaxf(a[4 * j4 + 1], 0.f), ww.y, sig);
-              sig = fmaf(fmaxf(a[4 * j4 + 2], 0.f), ww.z, sig); sig = fmaf(fmaxf(a[4 * j4 + 3], 0.f), ww.w, sig);
-            }
-          }
-          tmem_wait_st();
-          tc_fence_before();
-          arrive_leader(&a_kb[kb]);
-          if (tid == 0 && kb == 0) NERFW_STAMP(16 + layer * 8);
-          if (tid == 0 && kb == 3) NERFW_STAMP(17 + layer * 8);
-        }
-        if (layer == NERFW_SKIP + 1) {
-          if (!sigma_only) encode_dir(tile);
-          if (base + tstride < ntiles) encode_pos(tile + tstride);
-          if (tid == 0) NERFW_STAMP(90);   // encodings written
-        }
-      }
-      sig_part[cq * TM + row] = sig;
-      if (sigma_only) {
-        named_bar_sync(1, F_EPI_THREADS);
-        if (cq == 0 && live) {
-          const float sg = (sig_part[row] + sig_part[TM + row]) + (sig_part[2 * TM + row] + sig_part[3 * TM + row]) + vec[V_DENB];
-          raw[s] = make_float4(0.f, 0.f, 0.f, fmaxf(sg, 0.f));
-        }
-        continue;
-      }
-
-      // ---- direction-layer epilogue + rgb head (src/models.py:141-160) ----
-      mbar_wait(acc_full, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
-      if (tid == 0) NERFW_STAMP(91);   // direction-layer accumulator complete seen
-      float p3[3] = {0.f, 0.f, 0.f};
-      {
-        const uint32_t col = cq * 32;
-        uint32_t r[32];
-        tmem_ld32(tlane + COL_ACC + col, r);
-        tmem_wait_ld();
-        tc_fence_before();
-        arrive_leader(acc_free);   // the next tile's layer 0 may start
-        if (tid == 0) NERFW_STAMP(92);
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float hv = fmaxf(__uint_as_float(r[j]) + vec[V_DIRB + col + j], 0.f);
-          bits |= (hv > 0.f ? 1u : 0u) << j;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv, vec[V_RGBW + c * 128 + col + j], p3[c]);
-        }
-        if (masks && (!PAIR || tile < ntiles)) masks[mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))] = bits;
-      }
-      if (cq != 0) rgb_part[cq * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
-      named_bar_sync(1, F_EPI_THREADS);
-      if (cq == 0 && live) {
-        const float4 o1 = rgb_part[TM + row], o2 = rgb_part[2 * TM + row], o3 = rgb_part[3 * TM + row];
-        float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (app_off) off = __ldg(app_off + src.emb_row(s));
-        float sg = (sig_part[row] + sig_part[TM + row]) + (sig_part[2 * TM + row] + sig_part[3 * TM + row]) + vec[V_DENB];
-        float4 o;
-        o.x = 1.0f / (1.0f + expf(-(p3[0] + o1.x + o2.x + o3.x + vec[V_RGBB + 0] + off.x)));
-        o.y = 1.0f / (1.0f + expf(-(p3[1] + o1.y + o2.y + o3.y + vec[V_RGBB + 1] + off.y)));
-        o.z = 1.0f / (1.0f + expf(-(p3[2] + o1.z + o2.z + o3.z + vec[V_RGBB + 2] + off.z)));
-        o.w = fmaxf(sg, 0.f);
-        raw[s] = o;
-      }
-      if (tid == 0) NERFW_STAMP(93);   // tile written
-    }
-  }
-  // ---- teardown ----
-  tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();
-  if (warp == F_MMA_WARP) {
-    __syncwarp();
-    if (PAIR) tmem_dealloc_2cta<512>(tmem); else tmem_dealloc<512>(tmem);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // Self-test of the primitives: D (128 x N fp32) = A (128 x K bf16) * B (N x K bf16)^T for one CTA.
 // mode 0: A from shared memory (SS); mode 1: A from tensor memory (TS).  K multiple of 64 (<= 256), N multiple of 16.
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat16* __restrict__ A,
@@ -975,93 +563,6 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// Self-test of the CTA-pair MMA: D (256 x N fp32) = A (256 x K bf16) * B (N x K bf16)^T on a cluster of two CTAs.
-// CTA r holds rows 128 r .. 128 r + 127 of A (shared memory, mode 0, or tensor memory, mode 1) and of D, and rows
-// N/2 r .. of B.  Pins M = 256 instruction descriptors, the split of B and the multicast commit.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-umma_selftest_2cta_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, int N, int K, int mode,
-                          float* __restrict__ D, int reps, long long* __restrict__ cycles) {
-  extern __shared__ uint8_t smem_dyn[];
-  uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  uint8_t* sA = sm;                  // K/64 tiles of 128 x 128 B
-  uint8_t* sB = sm + 65536;          // K/64 tiles of N/2 x 128 B (16 KB stride)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 65536 + 65536);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t rank = cluster_ctarank();
-  const int nkb = K / 64, nh = N / 2;
-  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc_2cta<512>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  for (int idx = tid; idx < nh * K; idx += 128) {
-    int n = idx / K, k = idx % K;
-    *reinterpret_cast<__nv_bfloat16*>(sB + (k / 64) * 16384 + sw128_offset(n, k % 64)) = B[(size_t)(rank * nh + n) * K + k];
-  }
-  if (mode == 0) {
-    for (int idx = tid; idx < 128 * K; idx += 128) {
-      int m = idx / K, k = idx % K;
-      *reinterpret_cast<__nv_bfloat16*>(sA + (k / 64) * 16384 + sw128_offset(m, k % 64)) = A[(size_t)(rank * 128 + m) * K + k];
-    }
-  } else {
-    const uint32_t tl = tmem + ((warp * 32) << 16);
-    for (int c0 = 0; c0 < K / 2; c0 += 16) {
-      uint32_t pk[16];
-      for (int j = 0; j < 16; ++j) {
-        const __nv_bfloat16* a = A + (size_t)(rank * 128 + tid) * K + 2 * (c0 + j);
-        pk[j] = (uint32_t)__bfloat16_as_ushort(a[0]) | ((uint32_t)__bfloat16_as_ushort(a[1]) << 16);
-      }
-      tmem_st16(tl + COL_AHI + c0, pk);
-    }
-    tmem_wait_st();
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  if (rank == 0 && tid == 0) {
-    const uint32_t idesc = idesc_bf16(256, (uint32_t)N);
-    const long long c0 = clock64();
-    for (int rep = 0; rep < reps - 1; ++rep)   // timing only: the same chain issued back to back (results discarded below)
-      for (int kb = 0; kb < nkb; ++kb) {
-        uint64_t b = smem_desc_sw128(smem_u32(sB + kb * 16384));
-        uint64_t a = smem_desc_sw128(smem_u32(sA + kb * 16384));
-        for (int k = 0; k < 4; ++k) {
-          if (mode == 0) mma_ss_2cta(tmem + COL_ACC, a + 2 * k, b + 2 * k, idesc, 1u);
-          else mma_ts_2cta(tmem + COL_ACC, tmem + COL_AHI + 32 * kb + 8 * k, b + 2 * k, idesc, 1u);
-        }
-      }
-    if (cycles) cycles[1] = c0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      uint64_t b = smem_desc_sw128(smem_u32(sB + kb * 16384));
-      uint64_t a = smem_desc_sw128(smem_u32(sA + kb * 16384));
-      for (int k = 0; k < 4; ++k) {
-        uint32_t accf = (kb | k) ? 1u : 0u;
-        if (mode == 0) mma_ss_2cta(tmem + COL_ACC, a + 2 * k, b + 2 * k, idesc, accf);
-        else mma_ts_2cta(tmem + COL_ACC, tmem + COL_AHI + 32 * kb + 8 * k, b + 2 * k, idesc, accf);
-      }
-    }
-    mma_commit_2cta(bar);
-  }
-  mbar_wait(bar, 0);
-  tc_fence_after();
-  if (cycles && rank == 0 && tid == 0) cycles[0] = clock64() - cycles[1];
-  {
-    const uint32_t tl = tmem + ((warp * 32) << 16);
-    for (int c0 = 0; c0 < N; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tl + COL_ACC + c0, r);
-      tmem_wait_ld();
-      for (int j = 0; j < 32 && c0 + j < N; ++j) D[(size_t)(rank * 128 + tid) * N + c0 + j] = __uint_as_float(r[j]);
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 0) tmem_dealloc_2cta<512>(tmem);
-}
-
 }  // namespace tc
 
 size_t mlp_tc_packed_bytes() { return tc::PACKED_BYTES; }
@@ -1084,98 +585,49 @@ int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSou
                       int64_t n_total, int mode_flags, float* raw, void* relu_masks, cudaStream_t stream) {
   const int mode = mode_flags & 0xff;
   const bool x3 = mode == NERFW_MLP_BF16X3, f16 = mode == NERFW_MLP_FP16;
+  const bool sigma_only = (mode_flags & NERFW_MLP_SIGMA_ONLY) != 0;
   (void)w;
   static thread_local unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
   }
   int64_t ntiles = ceil_div64(n_total, tc::TM);
   int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
-  // kernel flags: bit 0 profiling switch (time the kernel without L2 weight traffic), bit 1 sigma-only output
-  const int dbg = (getenv("NERFW_FWD_SKIP_WEIGHTS") ? 1 : 0) | ((mode_flags & NERFW_MLP_SIGMA_ONLY) ? 2 : 0);
-  long long* timeline = nullptr;                              // profiling switch: device pointer (decimal) to 128 int64 slots
+  int dbg = 0;                     // kernel flags: bit 0 = profiling switch (reuse the ring contents; wrong results)
+  long long* timeline = nullptr;   // profiling: device pointer to 128 int64 clock64 slots
+#ifdef NERFW_PROFILE
+  // Only in the separate profiling build (make PROFILE=1 -> libnerfw_sm100_profile.so, used by scripts/): the product
+  // library never reads the environment.
+  if (getenv("NERFW_FWD_SKIP_WEIGHTS")) dbg |= 1;
   if (const char* t = getenv("NERFW_FWD_TIMELINE")) timeline = reinterpret_cast<long long*>(strtoull(t, nullptr, 10));
+#endif
   const float4* ao = reinterpret_cast<const float4*>(app_off);
   const size_t f16_off = mlp_tc_packed_f16_offset();
   float4* out = reinterpret_cast<float4*>(raw);
   uint32_t* mk = reinterpret_cast<uint32_t*>(relu_masks);
-  // CTA-pair kernel (cta_group::2): opt-in with NERFW_FWD_PAIR=1 while it is being validated; needs whole pairs of SMs
-  // and enough tiles to keep every pair busy
-  const bool pair = getenv("NERFW_FWD_PAIR") && atoi(getenv("NERFW_FWD_PAIR")) != 0 && ntiles >= 2 * (int64_t)sm_count() && !(dbg & 2);
-  if (pair) {
-    static thread_local unsigned long long attr_mask2 = 0;
-    if (first_use_on_device(attr_mask2)) {
-      NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-      NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-      NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(sm_count() & ~1));
-    cfg.blockDim = dim3(tc::F_THREADS);
-    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    long long* no_timeline = timeline;
-    const int no_dbg = dbg;
-    if (x3)
-      NERFW_CUDA(cudaLaunchKernelEx(&cfg, tc::mlp_tc_fwd_pair_kernel<true, false>, pk, src, ao, n_total, out, mk, no_dbg, no_timeline, f16_off));
-    else if (f16)
-      NERFW_CUDA(cudaLaunchKernelEx(&cfg, tc::mlp_tc_fwd_pair_kernel<false, true>, pk, src, ao, n_total, out, mk, no_dbg, no_timeline, f16_off));
-    else
-      NERFW_CUDA(cudaLaunchKernelEx(&cfg, tc::mlp_tc_fwd_pair_kernel<false, false>, pk, src, ao, n_total, out, mk, no_dbg, no_timeline, f16_off));
-  } else if (dbg & 2) {   // NERFW_MLP_SIGMA_ONLY
-    static thread_local unsigned long long attr_mask3 = 0;
-    if (first_use_on_device(attr_mask3)) {
-      NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-      NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-      NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    }
-    if (x3)
-      tc::mlp_tc_fwd_kernel<true, false, true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
-    else if (f16)
-      tc::mlp_tc_fwd_kernel<false, true, true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
-    else
-      tc::mlp_tc_fwd_kernel<false, false, true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
-  } else if (x3)
-    tc::mlp_tc_fwd_kernel<true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
-  else if (f16)
-    tc::mlp_tc_fwd_kernel<false, true><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
-  else
-    tc::mlp_tc_fwd_kernel<false><<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
+  auto launch = [&](auto kernel) {
+    kernel<<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
+  };
+  if (sigma_only) {
+    if (x3) launch(tc::mlp_tc_fwd_kernel<true, false, true>);
+    else if (f16) launch(tc::mlp_tc_fwd_kernel<false, true, true>);
+    else launch(tc::mlp_tc_fwd_kernel<false, false, true>);
+  } else {
+    if (x3) launch(tc::mlp_tc_fwd_kernel<true>);
+    else if (f16) launch(tc::mlp_tc_fwd_kernel<false, true>);
+    else launch(tc::mlp_tc_fwd_kernel<false>);
+  }
   NERFW_LAUNCHED();
   return NERFW_OK;
 }
 
 }  // namespace nerfw
-
-// D (256,n) = A (256,k) B (n,k)^T through one CTA-pair MMA chain (cta_group::2); tests only.
-extern "C" int nerfw_selftest_umma_2cta(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream) {
-  using namespace nerfw;
-  NERFW_REQUIRE(a_bf16 && b_bf16 && d, "nerfw_selftest_umma_2cta: null pointer");
-  NERFW_REQUIRE(n >= 32 && n <= 256 && n % 32 == 0, "nerfw_selftest_umma_2cta: N must be a multiple of 32 in [32,256]");
-  NERFW_REQUIRE(k >= 64 && k <= 256 && k % 64 == 0, "nerfw_selftest_umma_2cta: K must be a multiple of 64 in [64,256]");
-  NERFW_REQUIRE(mode == 0 || mode == 1, "nerfw_selftest_umma_2cta: mode must be 0 (SS) or 1 (TS)");
-  const size_t smem = 65536 + 65536 + 64 + 1024;
-  static thread_local unsigned long long attr_mask = 0;
-  if (first_use_on_device(attr_mask)) {
-    NERFW_CUDA(cudaFuncSetAttribute(tc::umma_selftest_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  tc::umma_selftest_2cta_kernel<<<2, 128, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(a_bf16),
-                                                                    reinterpret_cast<const __nv_bfloat16*>(b_bf16), n, k, mode, d,
-                                                                    getenv("NERFW_2CTA_REPS") ? atoi(getenv("NERFW_2CTA_REPS")) : 1,
-                                                                    getenv("NERFW_2CTA_CYCLES") ? reinterpret_cast<long long*>(strtoull(getenv("NERFW_2CTA_CYCLES"), nullptr, 10)) : nullptr);
-  NERFW_LAUNCHED();
-  return NERFW_OK;
-}
 
 // D = A B^T through tcgen05 for one 128-row tile; used by tests to pin descriptor / swizzle / TMEM layouts.
 extern "C" int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream) {

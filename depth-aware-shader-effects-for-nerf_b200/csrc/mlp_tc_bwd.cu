@@ -460,8 +460,18 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
 #pragma unroll
           for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv[j], vec[V_RGBW + c * 128 + dcol + j], p3[c]);
         }
+        if (src.emb_shared || !app_vec) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) ph_hdt[j] = pack_bf16x2(hv[2 * j] + appv[dcol + 2 * j], hv[2 * j + 1] + appv[dcol + 2 * j + 1]);
+          for (int j = 0; j < 16; ++j) ph_hdt[j] = pack_bf16x2(hv[2 * j] + appv[dcol + 2 * j], hv[2 * j + 1] + appv[dcol + 2 * j + 1]);
+        } else {  // per-ray embeddings: a = W_app e_ray + b_app, one 128-float row per ray (app_vec_kernel)
+          const float4* av = reinterpret_cast<const float4*>(app_vec + (live ? src.emb_row(s) : 0) * NERFW_DIR_HIDDEN + dcol);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 a4 = __ldg(av + j4);
+            ph_hdt[2 * j4] = pack_bf16x2(hv[4 * j4] + a4.x, hv[4 * j4 + 1] + a4.y);
+            ph_hdt[2 * j4 + 1] = pack_bf16x2(hv[4 * j4 + 2] + a4.z, hv[4 * j4 + 3] + a4.w);
+          }
+        }
         hmask = fwd_masks ? __ldg(fwd_masks + mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))) : bits;
       }
       tc_fence_before();
@@ -471,7 +481,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
       {
         const float4 q0 = rgb_part[row], q1 = rgb_part[TM + row], q2 = rgb_part[2 * TM + row], q3 = rgb_part[3 * TM + row];
         float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (app_off && live) off = __ldg(app_off);  // shared embedding only
+        if (app_off && live) off = __ldg(app_off + src.emb_row(s));
         float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live) dr = __ldg(d_raw + s);
         const float lg[3] = {(q0.x + q1.x) + (q2.x + q3.x) + vec[V_RGBB + 0] + off.x,
@@ -488,7 +498,12 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         if (cq == 0) {
           dsig_s[row] = ds;
           *reinterpret_cast<float4*>(tsc + (size_t)DLS_BLOCK * BLK + row * 16) = make_float4(dlog[0], dlog[1], dlog[2], ds);
-          if (dl_acc) {  // sum of d logits per (shared) embedding row: appearance gradients are finished from it
+          if (dl_acc && !src.emb_shared) {  // per-ray embeddings: sum of d logits per ray (<= n_per_ray adds per address)
+            if (live) {
+              float* acc = dl_acc + 4 * src.emb_row(s);
+              atomicAdd(acc + 0, dlog[0]); atomicAdd(acc + 1, dlog[1]); atomicAdd(acc + 2, dlog[2]);
+            }
+          } else if (dl_acc) {  // sum of d logits of the shared embedding row: appearance gradients are finished from it
             float a0 = dlog[0], a1 = dlog[1], a2 = dlog[2];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -862,13 +877,58 @@ __global__ void __launch_bounds__(128) app_bwd_shared_kernel(NerfwWeights w, Ner
   }
 }
 
-// a[k] = W_app e + b_app (128 floats) for the shared embedding
-__global__ void __launch_bounds__(128) app_vec_kernel(NerfwWeights w, const float* __restrict__ emb, float* __restrict__ out) {
+// a[row][k] = W_app e_row + b_app (128 floats per embedding row)
+__global__ void __launch_bounds__(128) app_vec_kernel(NerfwWeights w, const float* __restrict__ emb, int64_t rows,
+                                                      float* __restrict__ out) {
   const int k = threadIdx.x;
-  float a = __ldg(w.app_b + k);
-#pragma unroll 8
-  for (int q = 0; q < NERFW_APP_DIM; ++q) a = fmaf(__ldg(w.app_w + k * NERFW_APP_DIM + q), __ldg(emb + q), a);
-  out[k] = a;
+  float wk[NERFW_APP_DIM];
+#pragma unroll
+  for (int q = 0; q < NERFW_APP_DIM; ++q) wk[q] = __ldg(w.app_w + k * NERFW_APP_DIM + q);
+  const float bk = __ldg(w.app_b + k);
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    float a = bk;
+#pragma unroll
+    for (int q = 0; q < NERFW_APP_DIM; ++q) a = fmaf(wk[q], __ldg(emb + row * NERFW_APP_DIM + q), a);
+    out[row * NERFW_DIR_HIDDEN + k] = a;
+  }
+}
+
+// appearance branch, one embedding row per ray: per row r, G_r = W_rgb^T DL_r (DL_r = sum of the ray's d logits);
+// dW_app[k][q] += sum_r G_r[k] e_r[q]; db_app[k] += sum_r G_r[k]; d_emb[r][q] += sum_k G_r[k] W_app[k][q].
+// A CTA walks a contiguous block of rows with thread k keeping its row of dW_app in registers: one flush per CTA.
+__global__ void __launch_bounds__(128) app_bwd_rows_kernel(NerfwWeights w, NerfwGrads g, const float* __restrict__ emb,
+                                                           int64_t rows, const float* __restrict__ dl,
+                                                           float* __restrict__ d_emb) {
+  __shared__ float gk[NERFW_DIR_HIDDEN];
+  __shared__ float e[NERFW_APP_DIM];
+  const int k = threadIdx.x;
+  const float r0 = __ldg(w.rgb_w + k), r1 = __ldg(w.rgb_w + 128 + k), r2 = __ldg(w.rgb_w + 256 + k);
+  float acc[NERFW_APP_DIM];
+#pragma unroll
+  for (int q = 0; q < NERFW_APP_DIM; ++q) acc[q] = 0.f;
+  float bsum = 0.f;
+  const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t rbeg = blockIdx.x * per, rend = rbeg + per < rows ? rbeg + per : rows;
+  for (int64_t row = rbeg; row < rend; ++row) {
+    __syncthreads();   // previous row's gk / e consumed
+    if (k < NERFW_APP_DIM) e[k] = __ldg(emb + row * NERFW_APP_DIM + k);
+    const float G = dl[4 * row] * r0 + dl[4 * row + 1] * r1 + dl[4 * row + 2] * r2;
+    gk[k] = G;
+    __syncthreads();
+    bsum += G;
+#pragma unroll
+    for (int q = 0; q < NERFW_APP_DIM; ++q) acc[q] = fmaf(G, e[q], acc[q]);
+    if (d_emb && k < NERFW_APP_DIM) {
+      float de = 0.f;
+      for (int kk = 0; kk < NERFW_DIR_HIDDEN; ++kk) de = fmaf(gk[kk], __ldg(w.app_w + kk * NERFW_APP_DIM + k), de);
+      atomicAdd(d_emb + row * NERFW_APP_DIM + k, de);
+    }
+  }
+  if (rend > rbeg) {
+#pragma unroll
+    for (int q = 0; q < NERFW_APP_DIM; ++q) atomicAdd(g.app_w + k * NERFW_APP_DIM + q, acc[q]);
+    atomicAdd(g.app_b + k, bsum);
+  }
 }
 
 // MN-major self-test: D (128 x N) = At^T Bt with At (K x 128) and Bt (K x N) row-major bf16 (K, N multiples of 64)
@@ -978,13 +1038,16 @@ int launch_pack_weights_t(const NerfwWeights& w, void* packed, cudaStream_t stre
 
 using namespace nerfw;
 
+// workspace: [4096-byte header: shared-embedding app_off / dl_acc / app_vec][scratch tiles][per-ray appearance rows:
+// app_off float4 | dl_acc float4 | app_vec 128 floats, for n_rays rows (used when emb_rows == n_rays)]
+static size_t bwd_tc_rows_bytes(int64_t n_rays) { return (size_t)n_rays * (16 + 16 + NERFW_DIR_HIDDEN * sizeof(float)); }
 extern "C" size_t nerfw_mlp_bwd_tc_workspace_bytes(int64_t n_rays, int n_samples) {
   const int64_t total = n_rays * (int64_t)(n_samples > 0 ? n_samples : 1);
   const int64_t ntiles = ceil_div64(total, tc::TM);
-  return 4096 + (size_t)ntiles * tcb::TILE_BYTES;
+  return 4096 + (size_t)ntiles * tcb::TILE_BYTES + bwd_tc_rows_bytes(n_rays);
 }
 
-// Same contract as nerfw_mlp_bwd (include/nerfw.h), tensor-core arithmetic; shared (emb_rows == 1) or no embedding only.
+// Same contract as nerfw_mlp_bwd (include/nerfw.h), tensor-core arithmetic; no, one shared or one embedding row per ray.
 extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const float* pts_or_o, const float* dirs,
                                 const float* z, const float* emb, int64_t emb_rows, int64_t n_rays, int n_samples,
                                 const float* d_raw, const void* relu_masks, const NerfwGrads* grads, float* d_emb,
@@ -1000,7 +1063,8 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   NERFW_REQUIRE(pts_or_o && dirs && d_raw && workspace, "nerfw_mlp_bwd_tc: null pointer");
   NERFW_REQUIRE(aligned16(d_raw) && aligned16(workspace), "nerfw_mlp_bwd_tc: d_raw and workspace must be 16-byte aligned");
   if (emb) {
-    NERFW_REQUIRE(emb_rows == 1, "nerfw_mlp_bwd_tc: only a shared embedding (emb_rows == 1) is supported; use nerfw_mlp_bwd for per-ray embeddings");
+    NERFW_REQUIRE(emb_rows == 1 || emb_rows == n_rays, "nerfw_mlp_bwd_tc: emb_rows=%lld must be 1 or n_rays=%lld",
+                  (long long)emb_rows, (long long)n_rays);
     NERFW_REQUIRE(w->app_w && w->app_b && grads->app_w && grads->app_b, "nerfw_mlp_bwd_tc: embedding given but appearance parameters/gradients are null");
   }
   const size_t need = nerfw_mlp_bwd_tc_workspace_bytes(n_rays, z ? n_samples : 1);
@@ -1016,10 +1080,18 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   float* app_vec = reinterpret_cast<float*>(base + 64);
   uint8_t* scratch = base + 4096;
   NERFW_CUDA(cudaMemsetAsync(base, 0, 4096, st));
+  const bool per_ray = emb && emb_rows > 1;
+  if (per_ray) {   // one (app_off, dl_acc, app_vec) row per ray, behind the scratch tiles
+    uint8_t* rows_base = base + (need - bwd_tc_rows_bytes(n_rays));
+    app_off = reinterpret_cast<float*>(rows_base);
+    dl_acc = reinterpret_cast<float*>(rows_base + (size_t)n_rays * 16);
+    app_vec = reinterpret_cast<float*>(rows_base + (size_t)n_rays * 32);
+    NERFW_CUDA(cudaMemsetAsync(dl_acc, 0, (size_t)n_rays * 16, st));
+  }
   if (emb) {
-    int rc = launch_app_offset(*w, emb, 1, app_off, st);
+    int rc = launch_app_offset(*w, emb, emb_rows, app_off, st);
     if (rc) return rc;
-    tcb::app_vec_kernel<<<1, 128, 0, st>>>(*w, emb, app_vec);
+    tcb::app_vec_kernel<<<(unsigned)(emb_rows < 1184 ? emb_rows : 1184), 128, 0, st>>>(*w, emb, emb_rows, app_vec);
     NERFW_LAUNCHED();
   }
   SampleSource src;
@@ -1028,7 +1100,7 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   src.z = z;
   src.emb = emb;
   src.n_per_ray = z ? n_samples : 1;
-  src.emb_shared = 1;
+  src.emb_shared = per_ray ? 0 : 1;
   const int64_t total = n_rays * (z ? n_samples : 1);
   const int64_t ntiles = ceil_div64(total, tc::TM);
   NERFW_REQUIRE(ntiles < (1ll << 30), "nerfw_mlp_bwd_tc: too many samples");
@@ -1040,13 +1112,19 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   }
   const int sms = sm_count();
   int64_t grid1 = ntiles < sms ? ntiles : sms;
-  const int dbg_all = getenv("NERFW_WGRAD_DEBUG") ? atoi(getenv("NERFW_WGRAD_DEBUG")) : 0;  // profiling switches
+  int dbg_all = 0;                 // profiling switches (results are wrong when set)
+  long long* timeline = nullptr;   // profiling: device pointer to clock64 slots
+#ifdef NERFW_PROFILE
+  // Only in the separate profiling build (make PROFILE=1 -> libnerfw_sm100_profile.so): the product library never reads
+  // the environment.
+  if (const char* e = getenv("NERFW_WGRAD_DEBUG")) dbg_all = atoi(e);
+  if (const char* e = getenv("NERFW_BWD_TIMELINE")) timeline = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
+#endif
   if (!(dbg_all & 16))   // bit 4: wgrad kernel only
   tcb::mlp_tc_bwd_pass1_kernel<<<(unsigned)grid1, tcb::P1_THREADS, tcb::SMEM1_BYTES, st>>>(
       reinterpret_cast<const uint8_t*>(packed), src, emb ? reinterpret_cast<const float4*>(app_off) : nullptr,
       emb ? app_vec : nullptr, reinterpret_cast<const float4*>(d_raw), total, scratch, emb ? dl_acc : nullptr,
-      reinterpret_cast<const uint32_t*>(relu_masks), dbg_all,
-      getenv("NERFW_BWD_TIMELINE") ? reinterpret_cast<long long*>(strtoull(getenv("NERFW_BWD_TIMELINE"), nullptr, 10)) : nullptr);
+      reinterpret_cast<const uint32_t*>(relu_masks), dbg_all, timeline);
   NERFW_LAUNCHED();
 
   // ---- pass-2 plan: one weight block and one contiguous tile range per CTA, CTAs shared out by bytes per tile ----
@@ -1071,10 +1149,7 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   plan.d_density_b = grads->density_b;
   plan.d_rgb_w = grads->rgb_w;
   plan.d_rgb_b = grads->rgb_b;
-  {
-    const char* dbg = getenv("NERFW_WGRAD_DEBUG");  // profiling switch (scripts/time_bwd.py); results are wrong when set
-    plan.debug = dbg ? atoi(dbg) : 0;
-  }
+  plan.debug = dbg_all;
   double cost[13], csum = 0;
   for (int b = 0; b < nb; ++b) {
     const tcb::WgradBlock& wb = plan.blocks[b];
@@ -1125,7 +1200,11 @@ extern "C" int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const
   if (!(dbg_all & 8))    // bit 3: pass 1 only
   tcb::mlp_tc_wgrad_kernel<<<(unsigned)u, tcb::W2_THREADS, tcb::SMEM2_BYTES, st>>>(plan, scratch);
   NERFW_LAUNCHED();
-  if (emb) {
+  if (per_ray) {
+    const int64_t blocks = ceil_div64(emb_rows, 32);
+    tcb::app_bwd_rows_kernel<<<(unsigned)(blocks < 592 ? blocks : 592), 128, 0, st>>>(*w, *grads, emb, emb_rows, dl_acc, d_emb);
+    NERFW_LAUNCHED();
+  } else if (emb) {
     tcb::app_bwd_shared_kernel<<<1, 128, 0, st>>>(*w, *grads, emb, app_vec, dl_acc, d_emb);
     NERFW_LAUNCHED();
   }

@@ -54,8 +54,7 @@ constexpr uint32_t SM_VEC = SM_RING + NSTAGES * BIG_CHUNK;        // 196608
 constexpr uint32_t SM_SIG = SM_VEC + V_FLOATS * 4;                // [4][128] floats (density partial sums)
 constexpr uint32_t SM_RGB = SM_SIG + 4 * TM * 4;                  // [4][128] float4 (rgb logit partial sums)
 constexpr uint32_t SM_BAR = SM_RGB + 4 * TM * 16;                     // full[4], empty[4], acc_full, a_ready
-constexpr uint32_t SM_TMEMPTR = SM_BAR + (3 * 2 * (NSTAGES + 1) + 2 + 6) * 8;   // CTA-pair forward: 10 stages x (full, empty, pfull)
-// old: (2 * (NSTAGES + 1) + 2 + 6) * 8;   // + a_kb[4], acc_free, pe_ready; bf16 forward: 5 stages
+constexpr uint32_t SM_TMEMPTR = SM_BAR + 64 * 8;   // room for 64 mbarriers (forward: 2 x 5 ring + 2 + 4 + 2)
 constexpr uint32_t SM_TOTAL = SM_TMEMPTR + 16;
 constexpr size_t SMEM_BYTES = SM_TOTAL + 1024;  // slack for the manual 1024-byte alignment
 

@@ -6,7 +6,9 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnerfw_sm100.so")
+# NERFW_PROFILE_LIB=1 (scripts/ only): the separate profiling build (`make -C csrc PROFILE=1`), whose kernels honour the
+# timeline / skip switches.  The product library ignores the environment.
+LIB_PATH = os.path.join(_HERE, "libnerfw_sm100_profile.so" if os.environ.get("NERFW_PROFILE_LIB") == "1" else "libnerfw_sm100.so")
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
 N_LAYERS = 8
@@ -46,6 +48,8 @@ SIGNATURES = {
     "nerfw_ray_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "nerfw_sample_pdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nerfw_sample_pdf_general": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nerfw_posenc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nerfw_packed_bytes": (C.c_size_t, []),
     "nerfw_pack_weights": (C.c_int, [C.POINTER(NerfwWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -81,7 +85,6 @@ SIGNATURES = {
     "nerfw_hologram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p]),
     "nerfw_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "nerfw_selftest_umma_2cta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nerfw_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nerfw_selftest_umma_mn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }

@@ -1,7 +1,8 @@
 """torch.autograd glue: the MLP alone (NeRF.forward) and MLP + compositing (volume_render) as autograd Functions.
 
-Forward runs in the requested MLP mode; backward is composite_bwd (K7) followed by the fp32 MLP backward (K5), which
-recomputes the activations tile by tile instead of storing them.
+Forward runs in the requested MLP mode; backward is composite_bwd (K7) followed by the MLP backward (K5): the tcgen05
+kernels after a tensor-core forward (bf16 operands, gates from the forward's ReLU masks), the fp32 CUDA-core kernel after
+an fp32 forward.  Both recompute the activations tile by tile instead of storing them.
 """
 from __future__ import annotations
 
@@ -16,11 +17,11 @@ from ._lib import MLP_FP32
 
 
 def backward_uses_tensor_cores(mode: int, emb) -> bool:
-    """bf16 tcgen05 backward when the forward ran in a tensor-core mode and the embedding is shared (or absent);
-    NERFW_BWD_MODE=fp32 forces the fp32 CUDA-core backward."""
+    """bf16 tcgen05 backward whenever the forward ran in a tensor-core mode (no, one shared, or one embedding row per
+    ray / sample); NERFW_BWD_MODE=fp32 forces the fp32 CUDA-core backward."""
     if os.environ.get("NERFW_BWD_MODE", "bf16").lower() == "fp32":
         return False
-    return mode != MLP_FP32 and (emb is None or emb.shape[0] == 1)
+    return mode != MLP_FP32
 
 
 # Optional gradient sink: {parameter name: tensor}.  While set (nerfw.train.Trainer does, with views into its flat gradient

@@ -53,3 +53,53 @@ def aligned_spiral_poses(num_frames: int = 120, loops: int = 2, rotation_axis: s
 def blender_focal(width: int, camera_angle_x: float = 0.6911112070083618) -> float:
     """focal = 0.5 W / tan(0.5 camera_angle_x) (src/dataset.py:66; the Blender scenes' field of view)."""
     return 0.5 * width / np.tan(0.5 * camera_angle_x)
+
+
+def path_poses(camera_path: str = "circle", num_frames: int = 120, scene: str = "lego", spiral_loops: float = 2.0,
+               height_range=(-0.5, 0.5), radius: float = 4.0) -> np.ndarray:
+    """(num_frames,4,4) float32 poses of run.py::render_path (run.py:113-196): 'circle', 'spiral', 'horizontal_only'
+    (camera at (r sin t, height, r cos t)) and 'hemisphere' (golden-angle spiral over the upper hemisphere), looking at
+    the scene's centre -- (0, 0.5, 0) with Z up for lego, (0, 0.5, 0) for chair, the origin otherwise.  Unlike
+    look_at(), this driver normalises without the degenerate-case guards (run.py:182-189)."""
+    center = np.array([0.0, 0.0, 0.0])
+    up = np.array([0.0, 1.0, 0.0])
+    if scene == "lego":
+        center, up = np.array([0.0, 0.5, 0.0]), np.array([0.0, 0.0, 1.0])
+    elif scene == "chair":
+        center = np.array([0.0, 0.5, 0.0])
+    if camera_path == "circle":
+        theta = np.linspace(0, 2 * np.pi, num_frames)
+        heights = np.zeros_like(theta) + (0.5 if scene == "lego" else 0.0)
+        phi = np.zeros_like(theta)
+    elif camera_path == "spiral":
+        theta = np.linspace(0, 2 * np.pi * spiral_loops, num_frames)
+        hr = [0.3, 0.7] if scene == "lego" else list(height_range)
+        heights = np.linspace(hr[0], hr[1], num_frames)
+        phi = np.zeros_like(theta)
+    elif camera_path == "horizontal_only":
+        theta = np.linspace(0, 2 * np.pi * spiral_loops, num_frames)
+        heights = np.full_like(theta, 0.5)
+        phi = np.zeros_like(theta)
+    elif camera_path == "hemisphere":
+        idx = np.arange(0, num_frames, dtype=float) + 0.5
+        phi = np.arccos(1 - 2 * idx / num_frames) - np.pi / 2
+        theta = np.pi * (1 + 5 ** 0.5) * idx
+        heights = np.zeros_like(theta)
+    else:
+        raise ValueError(f"camera_path must be circle, spiral, horizontal_only or hemisphere, got {camera_path!r}")
+    poses = np.empty((num_frames, 4, 4), dtype=np.float32)
+    for i, angle in enumerate(theta):
+        if camera_path == "hemisphere":
+            pos = np.array([radius * np.cos(phi[i]) * np.sin(angle), radius * np.sin(phi[i]), radius * np.cos(phi[i]) * np.cos(angle)])
+        else:
+            pos = np.array([radius * np.sin(angle), heights[i], radius * np.cos(angle)])
+        fwd = center - pos
+        fwd = fwd / np.linalg.norm(fwd)
+        right = np.cross(fwd, up)
+        right = right / np.linalg.norm(right)
+        cup = np.cross(right, fwd)
+        cup = cup / np.linalg.norm(cup)
+        m = np.eye(4)
+        m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, cup, -fwd, pos
+        poses[i] = m.astype(np.float32)
+    return poses

@@ -124,7 +124,7 @@ def ray_points(rays_o: torch.Tensor, rays_d: torch.Tensor, z: torch.Tensor) -> t
 
 
 def sample_pdf(z_vals: torch.Tensor, weights: torch.Tensor, n_importance: int, u_rand: torch.Tensor,
-               want_aux: bool = False, want_zfine: bool = False):
+               want_aux: bool = False, want_zfine: bool = False, general_path: bool = False):
     z_vals = _f32c(z_vals, "z_vals")
     weights = _f32c(weights, "weights")
     u_rand = _f32c(u_rand, "u_rand")
@@ -143,9 +143,10 @@ def sample_pdf(z_vals: torch.Tensor, weights: torch.Tensor, n_importance: int, u
     if want_zfine and zf is None:
         zf = torch.empty((b, n_importance), dtype=torch.float32, device=dev)
     ulin = u_table(n_importance, dev)
+    fn = lib().nerfw_sample_pdf_general if general_path else lib().nerfw_sample_pdf
     with torch.cuda.device(dev):
-        check(lib().nerfw_sample_pdf(z_vals.data_ptr(), weights.data_ptr(), ulin.data_ptr(), u_rand.data_ptr(), b, n,
-                                     int(n_importance), out.data_ptr(), _ptr(inds), _ptr(zf), _ptr(cdf), _stream()))
+        check(fn(z_vals.data_ptr(), weights.data_ptr(), ulin.data_ptr(), u_rand.data_ptr(), b, n,
+                 int(n_importance), out.data_ptr(), _ptr(inds), _ptr(zf), _ptr(cdf), _stream()))
     if want_aux:
         return out, {"inds": inds, "z_fine": zf, "cdf": cdf}
     if want_zfine:
@@ -193,8 +194,11 @@ EXPECTED_SHAPES = {
 }
 
 
-def weights_struct(params: dict) -> _lib.NerfwWeights:
-    """Fill NerfwWeights/NerfwGrads from {state_dict key: contiguous fp32 CUDA tensor}.  Missing appearance -> NULL."""
+def weights_struct(params) -> _lib.NerfwWeights:
+    """Fill NerfwWeights/NerfwGrads from {state_dict key: contiguous fp32 CUDA tensor}.  Missing appearance -> NULL.
+    An already filled struct (NeRF.kernel_state() caches one per model) is passed through."""
+    if isinstance(params, _lib.NerfwWeights):
+        return params
     s = _lib.NerfwWeights()
     for i in range(8):
         s.pts_w[i] = params[f"pts_linears.{i}.weight"].data_ptr()
@@ -225,12 +229,29 @@ def check_params(params: dict) -> None:
             raise ValueError(f"{k} must be a contiguous float32 CUDA tensor (got {t.dtype} on {t.device})")
 
 
+_PACKED_BYTES = None
+_WS_BYTES: dict = {}
+
+
 def packed_bytes() -> int:
-    return int(lib().nerfw_packed_bytes())
+    global _PACKED_BYTES
+    if _PACKED_BYTES is None:
+        _PACKED_BYTES = int(lib().nerfw_packed_bytes())
+    return _PACKED_BYTES
 
 
-def pack_weights(params: dict, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    dev = params["rgb_linear.weight"].device
+def _mlp_workspace_bytes(n_rays: int, emb_rows: int) -> int:
+    key = (n_rays, emb_rows)
+    v = _WS_BYTES.get(key)
+    if v is None:
+        if len(_WS_BYTES) > 4096:
+            _WS_BYTES.clear()
+        v = _WS_BYTES[key] = int(lib().nerfw_mlp_workspace_bytes(n_rays, emb_rows))
+    return v
+
+
+def pack_weights(params, out: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
+    dev = device if device is not None else params["rgb_linear.weight"].device
     nbytes = packed_bytes()
     if out is None:
         out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -253,7 +274,7 @@ def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: to
     emb_rows = 0
     if emb is not None:
         emb_rows = emb.shape[0]
-    wbytes = int(lib().nerfw_mlp_workspace_bytes(n_rays, emb_rows))
+    wbytes = _mlp_workspace_bytes(n_rays, emb_rows)
     ws_buf = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     ws = weights_struct(params)
     masks = None
@@ -287,7 +308,7 @@ def mlp_bwd(params: dict, grads: dict, p: torch.Tensor, d: torch.Tensor, z: Opti
 def mlp_bwd_tc(params: dict, grads: dict, packed: torch.Tensor, p: torch.Tensor, d: torch.Tensor,
                z: Optional[torch.Tensor], emb: Optional[torch.Tensor], d_raw: torch.Tensor,
                d_emb: Optional[torch.Tensor], masks: Optional[torch.Tensor] = None) -> None:
-    """Tensor-core (bf16) backward; accumulates into `grads` and d_emb.  Shared or no embedding only.
+    """Tensor-core (bf16) backward; accumulates into `grads` and d_emb.  emb: None, (1,32) shared or (n_rays,32).
     masks: the ReLU gates returned by mlp_fwd(want_masks=True)."""
     dev = p.device
     n_rays = p.shape[0]
@@ -372,17 +393,6 @@ def selftest_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     d = torch.empty((128, b.shape[0]), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         check(lib().nerfw_selftest_umma(a.data_ptr(), b.data_ptr(), b.shape[0], a.shape[1], int(mode), d.data_ptr(), _stream()))
-    return d
-
-
-def selftest_umma_2cta(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
-    """D = A B^T for A (256,K), B (N,K) bf16 through one CTA-pair (cta_group::2) MMA chain on a 2-CTA cluster."""
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[0] == 256 and a.shape[1] == b.shape[1]
-    a = a.contiguous()
-    b = b.contiguous()
-    d = torch.empty((256, b.shape[0]), dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
-        check(lib().nerfw_selftest_umma_2cta(a.data_ptr(), b.data_ptr(), b.shape[0], a.shape[1], int(mode), d.data_ptr(), _stream()))
     return d
 
 

@@ -46,11 +46,26 @@ class RayBank:
         return {"rays_o": self.origins[idx].expand(self.H * self.W, 3), "rays_d": self.dirs[idx], "rgb": self.rgb[idx],
                 "alpha": None if self.alpha is None else self.alpha[idx], "appearance_idx": idx, "img_idx": idx}
 
-    def sample(self, batch_size: int, generator: Optional[torch.Generator] = None, img_idx: Optional[int] = None) -> dict:
-        """`batch_size` distinct random pixels of one random image (dataset.get_rays(), src/dataset.py:248-277)."""
+    def sample(self, batch_size: int, generator: Optional[torch.Generator] = None, img_idx: Optional[int] = None,
+               cross_image: bool = False) -> dict:
+        """A training batch with the keys of dataset.get_rays() (src/dataset.py:248-277).
+
+        cross_image=False (the reference's sampling): `batch_size` distinct random pixels of ONE random image;
+        'appearance_idx' is that image's index (an int), so the step uses one shared embedding row.
+        cross_image=True: `batch_size` random (image, pixel) pairs over the whole bank -- decorrelated batches, which the
+        reference's one-PNG-per-step loader cannot produce; 'appearance_idx' is then an int64 tensor (B,) and the step
+        gathers one embedding row per ray (the (B,D) case of src/render.py:39-44; forward and tcgen05 backward take
+        emb_rows == n_rays)."""
+        hw = self.H * self.W
+        if cross_image:
+            flat = torch.randint(0, self.n_images * hw, (batch_size,), generator=generator, device=self.device)
+            img = torch.div(flat, hw, rounding_mode="floor")
+            return {"rays_o": self.origins[img], "rays_d": self.dirs.reshape(-1, 3)[flat], "rgb": self.rgb.reshape(-1, 3)[flat],
+                    "alpha": None if self.alpha is None else self.alpha.reshape(-1, 1)[flat],
+                    "appearance_idx": img, "img_idx": img}
         if img_idx is None:
             img_idx = int(torch.randint(0, self.n_images, (1,), generator=generator, device=self.device))
-        sel = torch.randperm(self.H * self.W, generator=generator, device=self.device)[:batch_size]
+        sel = torch.randperm(hw, generator=generator, device=self.device)[:batch_size]
         return {"rays_o": self.origins[img_idx].expand(sel.numel(), 3), "rays_d": self.dirs[img_idx][sel],
                 "rgb": self.rgb[img_idx][sel], "alpha": None if self.alpha is None else self.alpha[img_idx][sel],
                 "appearance_idx": img_idx, "img_idx": img_idx}

@@ -40,6 +40,22 @@ class Trainer:
         self.exp_avg_sq = torch.zeros_like(self.flat.param)
         self.step_count = 0
 
+    def state_dict(self) -> dict:
+        """Adam state for checkpoints (tensors and numbers only; goes under 'optimizer_state_dict')."""
+        return {"kind": "nerfw.flat_adam", "step": int(self.step_count), "lr": float(self.lr), "betas": tuple(self.betas),
+                "eps": float(self.eps), "exp_avg": self.exp_avg.detach().cpu(), "exp_avg_sq": self.exp_avg_sq.detach().cpu(),
+                "offsets": list(self.flat.offsets)}
+
+    def load_state_dict(self, state: dict) -> None:
+        if state.get("kind") != "nerfw.flat_adam":
+            raise ValueError("not a nerfw Trainer state (a torch.optim.Adam state_dict belongs to torch.optim.Adam)")
+        if list(state["offsets"]) != list(self.flat.offsets):
+            raise ValueError("optimizer state was saved for a different parameter layout")
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        self.step_count = int(state["step"])
+        self.lr, self.betas, self.eps = float(state["lr"]), tuple(state["betas"]), float(state["eps"])
+
     def step(self, rays_o, rays_d, target, img_idx: Optional[int], near, far, n_samples, n_importance,
              perturb: bool = True, shard: bool = False, generator=None):
         """One optimisation step on this rank's rays.  shard=True: the arguments hold the GLOBAL batch and this rank
@@ -55,7 +71,13 @@ class Trainer:
         dev = self.flat.param.device
         emb = None
         if self.emb_table is not None and img_idx is not None:
-            emb = self.emb_table[img_idx]
+            if isinstance(img_idx, torch.Tensor) and img_idx.dim() > 0:      # one image index per ray (RayBank cross_image)
+                idx = img_idx.reshape(-1).to(dev)
+                if shard and world > 1:
+                    idx = idx[s:e]
+                emb = self.emb_table[idx]                                    # (B,32): per-ray rows, src/render.py:39-44
+            else:
+                emb = self.emb_table[int(img_idx)]
         self.flat.zero_grad()
         rgb, _, extras = volume_render(self.model, o, d, near, far, n_samples, n_importance, appearance_embedding=emb,
                                        perturb=perturb, mlp_dtype=self.mlp_dtype, generator=generator)
@@ -73,5 +95,5 @@ class Trainer:
         self.step_count += 1
         ops.adam_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
                       self.betas, self.eps, grad_scale=1.0 / world)
-        self.model._packed_key = None   # parameters changed behind autograd's back: rebuild the bf16 image lazily
+        self.model.invalidate_packed()   # the fused Adam kernel wrote the parameters through data_ptr: no _version bump
         return loss

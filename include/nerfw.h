@@ -123,6 +123,12 @@ int nerfw_ray_points(const float* rays_o, const float* rays_d, const float* z, i
 int nerfw_sample_pdf(const float* z_vals, const float* weights, const float* u_lin, const float* u_rand,
                      int64_t n_rays, int n_samples, int n_importance, float* z_out, int64_t* inds,
                      float* z_fine, float* cdf, void* stream);
+/* Same contract through the general path only (binary searches + ranking; no sorted-input shortcut).  The default entry
+ * point falls back to this path per ray whenever its assumptions fail; exported so the parity tests can compare the two
+ * bit for bit. */
+int nerfw_sample_pdf_general(const float* z_vals, const float* weights, const float* u_lin, const float* u_rand,
+                             int64_t n_rays, int n_samples, int n_importance, float* z_out, int64_t* inds,
+                             float* z_fine, float* cdf, void* stream);
 
 /* ---- PositionalEncoding.__call__ -- src/models.py:14-46 ----------------------------------------------
  * x (n,dim) -> out (n, dim*(include_input + 2*levels)): [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...]. */
@@ -156,8 +162,9 @@ int nerfw_mlp_bwd(const NerfwWeights* w, const float* pts_or_o, const float* dir
                   const NerfwGrads* grads, float* d_emb, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Tensor-core backward (bf16 operands, fp32 accumulation; stated looser bounds): same contract as nerfw_mlp_bwd, with
- * the packed weight cache of nerfw_pack_weights; supports no embedding or a shared one (emb_rows == 1).  The workspace
- * holds the per-tile activation / dZ scratch (1.16 MB per 128 samples).  relu_masks: the gates written by nerfw_mlp_fwd
+ * the packed weight cache of nerfw_pack_weights; emb_rows == 1 (shared) or == n_rays (one row per ray, the cross-image
+ * batches of src/dataset.py:248-277 with src/render.py:39-44).  The workspace holds the per-tile activation / dZ scratch
+ * (1.16 MB per 128 samples) and 544 bytes per ray for the per-ray appearance rows.  relu_masks: the gates written by nerfw_mlp_fwd
  * (recommended: gradients then follow the forward that produced the loss), or NULL to use the bf16 recompute's own. */
 size_t nerfw_mlp_bwd_tc_workspace_bytes(int64_t n_rays, int n_samples);
 int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const float* pts_or_o, const float* dirs, const float* z,
@@ -234,8 +241,6 @@ int nerfw_hologram(const uint8_t* image, const float* mag, const float* mag_max,
 /* Primitive self-test (tests only): D (128,n) fp32 = A (128,k) bf16 * B (n,k) bf16 ^T through one tcgen05 tile;
  * mode 0 = A from shared memory, 1 = A from tensor memory.  Pins the descriptor / swizzle / TMEM layouts. */
 int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream);
-/* CTA-pair form (tcgen05 cta_group::2 on a 2-CTA cluster): D (256,n) = A (256,k) * B (n,k)^T, B split by n over the pair. */
-int nerfw_selftest_umma_2cta(const void* a_bf16, const void* b_bf16, int n, int k, int mode, float* d, void* stream);
 /* Same with both operands MN-major (the wgrad form): D (128,n) = At^T Bt for At (k,128), Bt (k,n) bf16 row-major. */
 int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, int n, int k, float* d, void* stream);
 /* Tensor-pipe issue-rate probe: device cycles (int64 at cycles_dev) for reps x 16 MMAs of shape 128 x n x 16;

@@ -81,6 +81,31 @@ def render(sd, o, d, emb, coarse, fine, u):
     return rf, df, wf.sum(1)
 
 
+def render_reuse(sd, o, d, emb, coarse, fine, u):
+    """The reuse_coarse path of nerfw.render: the coarse pass's (rgb, sigma) records are kept for the 64 coarse depths,
+    only the 128 new depths go through the fine-pass arithmetic, and the merged row is composited."""
+    b = o.shape[0]
+    z, _ = orc.stratified_depths(o, d, 2.0, 6.0, 64, perturb=False)
+
+    def raw(z, lin):
+        n = z.shape[1]
+        pts = o[:, None] + d[:, None] * z[..., None]
+        dirs = d[:, None].expand(-1, n, -1).reshape(-1, 3)
+        rgb, sig = mlp(sd, pts.reshape(-1, 3), dirs, emb, lin)
+        return rgb.reshape(b, n, 3), sig.reshape(b, n, 1)
+    rgb_c, sig_c = raw(z, make_linear(coarse))
+    _, _, wc = orc.composite(sig_c, rgb_c, z)
+    _, _, aux = orc.resample_pdf(o, d, z, wc.squeeze(-1), 128, u_rand=u, return_aux=True)
+    z_new = aux["z_fine"]
+    rgb_f, sig_f = raw(z_new, make_linear(fine))
+    z_cat = torch.cat([z, z_new], -1)
+    z_all, order = torch.sort(z_cat, dim=-1, stable=True)
+    rgb_all = torch.gather(torch.cat([rgb_c, rgb_f], 1), 1, order[..., None].expand(-1, -1, 3))
+    sig_all = torch.gather(torch.cat([sig_c, sig_f], 1), 1, order[..., None])
+    rf, df, wf = orc.composite(sig_all, rgb_all, z_all)
+    return rf, df, wf.sum(1)
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     h = w = 48
@@ -91,7 +116,10 @@ def main():
     u = torch.rand(o.shape[0], 128, generator=g)
     emb = torch.randn(32, generator=g)
     combos = [("bf16x3", "bf16x3"), ("bf16x3", "fp16"), ("bf16x3", "bf16"), ("fp16", "bf16x3"), ("bf16", "bf16x3"),
-              ("bf16", "bf16"), ("fp16", "fp16"), ("fp16_x1_w2", "fp16_x1_w2"), ("fp16_x2_w1", "fp16_x2_w1")]
+              ("bf16", "bf16"), ("fp16", "fp16"), ("fp16_x1_w2", "fp16_x1_w2"), ("fp16_x2_w1", "fp16_x2_w1"),
+              ("fp16_x1_w2", "fp16"), ("fp16_x2_w1", "fp16")]
+    if len(sys.argv) > 1:   # e.g. "bf16x3:fp16,fp16:fp16"
+        combos = [tuple(c.split(":")) for c in sys.argv[1].split(",")]
     for variant in ("random-init", "dense x200", "dense x30"):
         sd = orc.make_state_dict(0)
         if variant != "random-init":
@@ -105,7 +133,10 @@ def main():
             e = [float((a - b).abs().max()) for a, b in zip(got, ref)]
             m = [float((a - b).abs().mean()) for a, b in zip(got, ref)]
             print(f"  coarse {coarse:11s} fine {fine:11s} max rgb {e[0]:.2e} depth {e[1]:.2e} acc {e[2]:.2e} | "
-                  f"mean rgb {m[0]:.1e} depth {m[1]:.1e} acc {m[2]:.1e}")
+                  f"mean rgb {m[0]:.1e} depth {m[1]:.1e} acc {m[2]:.1e}", flush=True)
+            got = render_reuse(sd, o, d, emb, coarse, fine, u)
+            e = [float((a - b).abs().max()) for a, b in zip(got, ref)]
+            print(f"     reuse_coarse (64 coarse records kept + 128 new)  max rgb {e[0]:.2e} depth {e[1]:.2e} acc {e[2]:.2e}", flush=True)
 
 
 if __name__ == "__main__":

@@ -219,8 +219,29 @@ def main():
     with torch.no_grad():
         rgb_h, depth_h, ex_h = orc.render_hier(sd, sd, oc, dc, 2.0, 6.0, 64, 128, emb=emb, perturb=False, u_rand=u_fix)
     np.savez_compressed(os.path.join(OUT, "crop32_hier.npz"), rgb=rgb_h.numpy(), depth=depth_h.numpy(),
-                        acc=ex_h["acc"].numpy(), z_vals=ex_h["z_vals"].numpy(), u_rand=u_fix.numpy())
+                        acc=ex_h["acc"].numpy(), z_vals=ex_h["z_vals"].numpy(), u_rand=u_fix.numpy(),
+                        inds=ex_h["inds"].numpy().astype(np.int16))
     man["cases"]["crop32_hier"] = {"sum_rgb": float(rgb_h.double().sum()), "sum_depth": float(depth_h.double().sum())}
+
+    # ---- DENSE hierarchical case (density head x200, bias +1: acc ~ 1 like a trained, opaque scene), centre 24x24 crop,
+    #      64 + 128, fixed u.  The coarse half is the reference's own volume_render (asserted bit-equal here);
+    #      resampling + fine pass are the composed oracle of SURVEY.md section 8c.
+    torch.manual_seed(34)
+    u_d = torch.rand(24 * 24, 128)
+    od = ro[38:62, 38:62].reshape(-1, 3).contiguous()
+    dd_ = rd[38:62, 38:62].reshape(-1, 3).contiguous()
+    with torch.no_grad(), quiet():
+        rgb_c_ref, depth_c_ref, ex_c_ref = volume_render(model_d, od, dd_, 2.0, 6.0, 64, 0, appearance_embedding=emb, perturb=False)
+    with torch.no_grad():
+        rgb_hd, depth_hd, ex_hd = orc.render_hier(sd_dense, sd_dense, od, dd_, 2.0, 6.0, 64, 128, emb=emb, perturb=False, u_rand=u_d)
+    assert torch.equal(ex_hd["rgb_coarse"], rgb_c_ref) and torch.equal(ex_hd["depth_coarse"], depth_c_ref)
+    assert torch.equal(ex_hd["weights_coarse"], ex_c_ref["weights"])
+    np.savez_compressed(os.path.join(OUT, "crop24_dense_hier.npz"), rgb=rgb_hd.numpy(), depth=depth_hd.numpy(),
+                        acc=ex_hd["acc"].numpy(), z_vals=ex_hd["z_vals"].numpy(), u_rand=u_d.numpy(),
+                        inds=ex_hd["inds"].numpy().astype(np.int16), depth_coarse=depth_c_ref.numpy(),
+                        weights_coarse=ex_hd["weights_coarse"][..., 0].numpy())
+    man["cases"]["crop24_dense_hier"] = {"mean_acc": float(ex_hd["acc"].mean()), "sum_depth": float(depth_hd.double().sum()),
+                                         "frac_last_bin": float((ex_hd["inds"] >= 64).float().mean())}
 
     # ---- gradients of the coarse path (autograd through the reference), 64 rays
     sel64 = torch.arange(0, 10000, 157)[:64]

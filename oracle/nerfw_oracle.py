@@ -230,9 +230,10 @@ def render_hier(sd_coarse, sd_fine, rays_o, rays_d, near, far, n_samples, n_impo
     d = torch.nn.functional.normalize(rays_d.reshape(-1, 3), dim=-1)
     z, _ = stratified_depths(o, d, near, far, n_samples, perturb=perturb, t_rand=t_rand)
     rgb_c, depth_c, w_c = shade(sd_coarse, o, d, z, emb)
-    z_all, _ = resample_pdf(o, d, z, w_c.squeeze(-1).detach(), n_importance, u_rand=u_rand)
+    z_all, _, aux = resample_pdf(o, d, z, w_c.squeeze(-1).detach(), n_importance, u_rand=u_rand, return_aux=True)
     rgb_f, depth_f, w_f = shade(sd_fine, o, d, z_all, emb)
     extras = {
+        "inds": aux["inds"], "z_fine": aux["z_fine"],
         "weights": w_f, "z_vals": z_all, "acc": w_f.sum(dim=1),
         "rgb_coarse": rgb_c.reshape(*shape[:-1], 3), "depth_coarse": depth_c.reshape(*shape[:-1], 1),
         "weights_coarse": w_c, "z_vals_coarse": z,

@@ -34,7 +34,8 @@ def test_host_only_entry_points():
     fwd = 2 * (30 * 32768 + 5 * 16384) + 2824 * 4
     # + the transposed (dgrad) image: 30 chunks of 32 KB, 1024-aligned; + the fp16 forward image (one copy per chunk)
     assert L.nerfw_packed_bytes() == (fwd + 1023) // 1024 * 1024 + 30 * 32768 + (30 * 32768 + 5 * 16384)
-    assert L.nerfw_mlp_bwd_tc_workspace_bytes(4096, 64) == 4096 + (4096 * 64 // 128) * 71 * 16384
+    # header + 71 scratch blocks of 16 KB per 128-sample tile + 544 bytes per ray (per-ray appearance rows)
+    assert L.nerfw_mlp_bwd_tc_workspace_bytes(4096, 64) == 4096 + (4096 * 64 // 128) * 71 * 16384 + 4096 * 544
     assert L.nerfw_mlp_workspace_bytes(4096, 1) >= 16
     assert L.nerfw_mlp_workspace_bytes(4096, 4096) >= 16 * 4096
     assert L.nerfw_launch_count() == 0 or L.nerfw_launch_count() > 0

@@ -1,0 +1,260 @@
+"""The reference's CALLERS against this repo's drop-in: camera paths, driver loops, file names, the training step.
+
+Goldens come from oracle/make_golden_callers.py, which executes the reference's unmodified drivers (render_aligned_spiral.py,
+run.py::render_path, src/train.py::train_nerf) with their own src/ on the CPU and records what they computed.  The GPU
+box has no reference tree, so the GPU tests replay the drivers' calling pattern through `src.ray_utils` / `src.render` /
+`src.models` (this repo's shim under the reference's module paths) and compare with those recordings.  Where the reference
+tree IS present (the CPU container), one more test imports the unmodified driver files with the shim shadowing the
+reference's `src` and checks that they bind to this repo's implementations.
+"""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, ROOT
+from gpu_util import maxabs, record
+
+REF = os.environ.get("NERFW_REFERENCE", "/root/reference")
+
+
+# ------------------------------------------------------------------------------------------------- CPU: camera paths
+def test_aligned_spiral_poses_match_reference_driver(golden):
+    """nerfw.camera.aligned_spiral_poses == every c2w render_aligned_spiral.py:27-122 hands to get_rays (captured from the
+    running reference driver), bit for bit: 120 frames x rotation axes x / y / z / none x scenes chair / lego."""
+    from nerfw.camera import aligned_spiral_poses
+    g = golden("callers_poses")
+    for scene in ("chair", "lego"):
+        for axis in ("x", "y", "z", "none"):
+            assert np.array_equal(aligned_spiral_poses(120, 2, axis, scene), g[f"{scene}_{axis}"]), (scene, axis)
+    assert np.array_equal(aligned_spiral_poses(7, 1, "x", "chair"), g["chair_x_7f_1loop"])
+
+
+def test_run_py_camera_paths_match_reference_driver(golden):
+    """nerfw.camera.path_poses == the c2w of run.py::render_path (run.py:113-196) for all four path types and the scene
+    special cases -- including the frames where the reference itself produces NaN (lego: forward parallel to up)."""
+    from nerfw.camera import path_poses
+    g = golden("callers_poses")
+    with np.errstate(invalid="ignore"):
+        for scene in ("lego", "chair", "hotdog"):
+            for path in ("circle", "spiral", "horizontal_only", "hemisphere"):
+                got = path_poses(path, 24, scene, 1.5, [-0.4, 0.6])
+                assert np.array_equal(got, g[f"run_{scene}_{path}"], equal_nan=True), (scene, path)
+    assert list(g["run_file_names"]) == [f"rgb_{i:03d}.png" for i in range(4)]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_unmodified_drivers_bind_to_the_shim():
+    """With this package's directory BEFORE the reference on sys.path, the reference's own driver files (render_aligned_spiral.py,
+    run.py, src/train.py, src/dataset.py) import unmodified and their `get_rays` / `volume_render` / `NeRF` names are this
+    repo's objects, while the modules off the hot path stay the reference's (run in a subprocess: module caches stay clean)."""
+    code = textwrap.dedent(f"""
+        import sys, types
+        mpl = types.ModuleType("matplotlib"); plt = types.ModuleType("matplotlib.pyplot"); mpl.pyplot = plt
+        sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = plt
+        sys.path.insert(0, {REF!r}); sys.path.insert(0, {PKG!r})
+        import nerfw
+        import render_aligned_spiral as ras
+        assert ras.__file__.startswith({REF!r}), ras.__file__
+        assert ras.get_rays is nerfw.get_rays and ras.volume_render is nerfw.volume_render and ras.NeRF is nerfw.NeRF
+        import src.render, src.models, src.ray_utils, src.dataset, src.train
+        assert src.render.__file__.startswith({PKG!r})
+        assert src.ray_utils.sample_importance is nerfw.sample_importance and src.models.PositionalEncoding is nerfw.PositionalEncoding
+        # everything off the hot path is still the reference's own module; its relative imports bind to the kernels
+        assert src.dataset.__file__.startswith({REF!r}) and src.train.__file__.startswith({REF!r})
+        assert src.train.volume_render is nerfw.volume_render and src.train.NeRF is nerfw.NeRF
+        import run
+        assert run.__file__.startswith({REF!r}) and run.volume_render is nerfw.volume_render and run.train_nerf is src.train.train_nerf
+        print("bound")
+    """)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "bound" in out.stdout, out.stderr[-2000:]
+
+
+def test_checkpoint_reads_reference_schema(tmp_path):
+    """A file written the way src/train.py:113-125 / run.py:296-312 write it (state_dict, torch.optim.Adam state, an
+    nn.Parameter embedding table) loads with weights_only=True semantics; shapes are checked."""
+    from config import Config
+    import nerfw
+    from nerfw.checkpoint import load_checkpoint
+    torch.manual_seed(3)
+    m = nerfw.NeRF(Config())
+    table = torch.nn.Parameter(torch.randn(4, 32))
+    opt = torch.optim.Adam(list(m.parameters()) + [table], lr=5e-4)
+    for p in list(m.parameters()) + [table]:
+        p.grad = torch.zeros_like(p)
+    opt.step()
+    path = str(tmp_path / "checkpoint_final.pt")
+    torch.save({"model_state_dict": m.state_dict(), "optimizer_state_dict": opt.state_dict(), "loss": 0.25, "psnr": 6.0,
+                "iteration": 30000, "appearance_embeddings": table}, path)            # run.py stores the Parameter itself
+    m2 = nerfw.NeRF(Config())
+    t2 = torch.nn.Parameter(torch.zeros(4, 32))
+    before = t2.data_ptr()
+    ck = load_checkpoint(path, m2, t2)
+    assert ck["iteration"] == 30000 and t2.data_ptr() == before and torch.equal(t2.detach(), table.detach())
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    with pytest.raises(RuntimeError, match="shape|expected"):
+        load_checkpoint(path, m2, torch.nn.Parameter(torch.zeros(5, 32)))
+
+
+# ------------------------------------------------------------------------------------------------- GPU: driver loops
+class _Dataset:
+    """The attributes the drivers read (src/dataset.py:60-85); same recipe as oracle/make_golden_callers.py::StubDataset."""
+
+    def __init__(self, h, w, emb_table, batch=None):
+        self.H, self.W = h, w
+        self.focal = 0.5 * w / np.tan(0.5 * 0.6911112070083618)
+        self.near, self.far = 2.0, 6.0
+        self.appearance_embeddings = torch.nn.Parameter(torch.from_numpy(emb_table).clone())   # lives on the CPU, like the reference's
+        self.batch = batch
+
+    def __len__(self):
+        return self.appearance_embeddings.shape[0]
+
+    def get_rays(self, idx=None, batch_size=None):
+        return self.batch
+
+
+def _seed0_model():
+    from config import Config
+    from src.models import NeRF                       # the reference's module path, this repo's class
+    cfg = Config()
+    cfg.device = torch.device("cuda")
+    torch.manual_seed(0)
+    return NeRF(cfg).to(cfg.device), cfg
+
+
+@pytest.mark.gpu
+def test_spiral_driver_chunk_loop_and_files(golden, tmp_path, monkeypatch):
+    """(a) The body of render_aligned_spiral.py:124-175 as its author wrote the calls -- get_rays on a device c2w, 4096-ray
+    chunks through volume_render, `.cpu()` per chunk, uint8 conversion -- through the src/ shim, against the PNGs the
+    reference driver wrote on the CPU (coarse only: the reference's n_importance branch is `pass`, so fine_pass=False
+    is the like-for-like setting).  (b) nerfw.frame.render_spiral_to_dir writes the same file names with the same pixels."""
+    from PIL import Image
+    from src.ray_utils import get_rays
+    from src.render import volume_render
+    from nerfw.camera import aligned_spiral_poses
+    from nerfw.frame import render_spiral_to_dir
+    g = golden("callers_spiral")
+    model, cfg = _seed0_model()
+    cfg.scene, cfg.num_samples, cfg.num_importance = "chair", 64, 128
+    ds = _Dataset(24, 24, g["emb_table"])
+    poses = aligned_spiral_poses(3, 1, "x", "chair")
+    monkeypatch.setenv("NERFW_COARSE_ONLY", "1")     # how an unmodified driver selects the reference's coarse-only output
+    worst = 0
+    for i in range(3):
+        c2w = torch.tensor(poses[i], dtype=torch.float32).to(cfg.device)
+        rays_o, rays_d = get_rays(ds.H, ds.W, ds.focal, c2w)
+        emb = ds.appearance_embeddings[0].to(cfg.device)
+        rgb_chunks, depth_chunks = [], []
+        with torch.no_grad():
+            for j in range(0, ds.H * ds.W, 200):
+                rgb_c, depth_c, _ = volume_render(model, rays_o.reshape(-1, 3)[j:j + 200].to(cfg.device),
+                                                  rays_d.reshape(-1, 3)[j:j + 200].to(cfg.device), near=ds.near, far=ds.far,
+                                                  n_samples=cfg.num_samples, n_importance=cfg.num_importance,
+                                                  appearance_embedding=emb, perturb=False)
+                rgb_chunks.append(rgb_c.cpu())
+                depth_chunks.append(depth_c.cpu())
+        rgb = torch.cat(rgb_chunks, dim=0).reshape(ds.H, ds.W, 3)
+        img = (rgb * 255).numpy().astype(np.uint8)
+        want = g[f"frame_{i:04d}_png"]
+        worst = max(worst, int(np.abs(img.astype(int) - want.astype(int)).max()))
+        if i == 0:
+            depth = torch.cat(depth_chunks, dim=0).reshape(ds.H, ds.W).numpy()
+            d8 = ((depth - depth.min()) / (depth.max() - depth.min()) * 255).astype(np.uint8)
+            worst = max(worst, int(np.abs(d8.astype(int) - g["depth_0000_png"].astype(int)).max()))
+    record("callers_spiral_chunk_loop", worst_grey_level=worst)
+    assert worst <= 1          # truncation to uint8: values within 1e-3/255 of an integer boundary may land one level apart
+    monkeypatch.chdir(tmp_path)
+    files = render_spiral_to_dir(model, ds, cfg, "spiral", num_frames=3, loops=1, rotation_axis="x", fine_pass=False)
+    names = sorted(os.path.relpath(f, os.path.join("output", "spiral")) for f in files)
+    assert names == sorted(str(n) for n in g["files"])
+    for n in names:
+        got = np.asarray(Image.open(os.path.join("output", "spiral", n)))
+        want = g[n.replace(".", "_")]
+        assert got.shape == want.shape and int(np.abs(got.astype(int) - want.astype(int)).max()) <= 1, n
+
+
+@pytest.mark.gpu
+def test_run_py_model_smoke_calls():
+    """run.py:327-345: bare model(positions, directions) and model(positions, directions, (1,32) embedding) on 10 points."""
+    import torch.nn.functional as F
+    model, cfg = _seed0_model()
+    test_positions = torch.randn(10, 3).to(cfg.device)
+    test_directions = F.normalize(torch.randn(10, 3).to(cfg.device), dim=-1)
+    with torch.no_grad():
+        rgb, sigma = model(test_positions, test_directions)
+    assert rgb.shape == (10, 3) and sigma.shape == (10, 1)
+    rgb, sigma = model(test_positions, test_directions, torch.randn(1, cfg.appearance_dim).to(cfg.device))
+    assert rgb.shape == (10, 3) and sigma.shape == (10, 1) and rgb.requires_grad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", None])
+def test_train_nerf_steps_match_reference(golden, monkeypatch, mode):
+    """Three iterations of src/train.py:54-92 exactly as written there -- torch.optim.Adam over model.parameters() plus the
+    CPU-resident dataset.appearance_embeddings, volume_render(perturb=True), mse_loss, backward, step -- through the shim,
+    with the uniforms the reference drew (torch.rand patched to replay them), against the losses / parameters the
+    reference's train_nerf produced on the CPU.  fp32 mode: losses within 2e-6; default mode (tensor cores): 2e-4."""
+    import torch.nn as nn
+    import torch.optim as optim
+    from src.render import volume_render
+    g = golden("callers_train")
+    model, cfg = _seed0_model()
+    cfg.num_samples, cfg.num_importance = 64, 128
+    batch = {"rays_o": torch.from_numpy(g["rays_o"]), "rays_d": torch.from_numpy(g["rays_d"]), "rgb": torch.from_numpy(g["target"]),
+             "appearance_idx": 1}
+    ds = _Dataset(24, 24, g["emb_table0"], batch)
+    if mode is not None:
+        monkeypatch.setenv("NERFW_MLP_MODE", mode)
+        import nerfw.models
+        monkeypatch.setattr(nerfw.models, "DEFAULT_MLP_MODE", mode)
+    monkeypatch.setenv("NERFW_COARSE_ONLY", "1")
+    params = list(model.parameters())
+    params.append(ds.appearance_embeddings)
+    optimizer = optim.Adam(params, lr=cfg.learning_rate)
+    draws = [torch.from_numpy(t) for t in g["t_rand"]]
+    real_rand = torch.rand
+
+    def replay(*shape, **kw):
+        t = draws.pop(0)
+        dev = kw.get("device", "cpu")
+        return t.to(dev)
+
+    losses = []
+    for i in range(1, 4):
+        b = ds.get_rays(batch_size=64)
+        rays_o, rays_d, target_rgb = b["rays_o"].to(cfg.device), b["rays_d"].to(cfg.device), b["rgb"].to(cfg.device)
+        appearance_embedding = ds.appearance_embeddings[b["appearance_idx"]].to(cfg.device)
+        monkeypatch.setattr(torch, "rand", replay)
+        try:
+            rgb, depth, extras = volume_render(model, rays_o, rays_d, near=ds.near, far=ds.far, n_samples=cfg.num_samples,
+                                               n_importance=cfg.num_importance, appearance_embedding=appearance_embedding,
+                                               perturb=True)
+        finally:
+            monkeypatch.setattr(torch, "rand", real_rand)
+        loss = nn.functional.mse_loss(rgb, target_rgb)
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        losses.append(loss.item())
+    want = g["losses"]
+    rel = max(abs(a - b) / b for a, b in zip(losses, want))
+    tol = 2e-6 if mode == "fp32" else 2e-4
+    sd = model.state_dict()
+    norms = np.array([float(sd[str(k)].double().norm()) for k in g["param_names"]])
+    norm_rel = float(np.max(np.abs(norms - g["param_norms"]) / (g["param_norms"] + 1e-12)))
+    emb_err = maxabs(ds.appearance_embeddings.detach(), g["emb_table"])
+    record(f"callers_train_{mode or 'default'}", loss_rel=rel, norm_rel=norm_rel, emb_abs=emb_err,
+           rgb_bias=maxabs(sd["rgb_linear.bias"], g["rgb_bias"]))
+    assert rel <= tol, (losses, list(want))
+    assert ds.appearance_embeddings.grad is not None and not ds.appearance_embeddings.is_cuda   # the CPU leaf got its gradient
+    assert float(np.abs(g["emb_table"][1] - g["emb_table0"][1]).max()) > 0                       # ... and the reference moved row 1
+    # Adam moves every element by ~lr per step regardless of gradient size: after 3 steps parameters agree to a few lr
+    assert emb_err <= 3 * 2 * cfg.learning_rate and maxabs(sd["rgb_linear.bias"], g["rgb_bias"]) <= 3 * 2 * cfg.learning_rate
+    assert norm_rel <= 1e-3
+    assert torch.equal(ds.appearance_embeddings.detach()[0], torch.from_numpy(g["emb_table0"][0]))  # untouched rows stay

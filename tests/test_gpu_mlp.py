@@ -139,9 +139,17 @@ def test_packed_cache_tracks_parameter_updates(cuda_model):
     assert torch.equal(a, c)
 
 
-def test_mlp_backward_vs_oracle_autograd(cuda_model, oracle, state_dict):
+# Stated bounds of the backward kernels against float64 autograd through the oracle: (max-abs error / max-abs gradient per
+# tensor, cosine per tensor).  fp32 CUDA-core kernel: summation order only.  Default path (forward bf16x3, tcgen05 backward
+# with bf16 operands and fp32 accumulation, gates from the forward): bf16 operand rounding, 2^-9 per product.
+BWD_TOL = {"fp32": (2e-4, 0.9999999), None: (3e-2, 0.9999)}
+
+
+@pytest.mark.parametrize("mode", ["fp32", None])
+def test_mlp_backward_vs_oracle_autograd(cuda_model, oracle, state_dict, mode):
     """All 24 parameter gradients + the embedding gradient of sum(raw * cotangent), vs autograd through the oracle
-    in float64 on the same inputs.  Bound: 2e-4 of each tensor's max-abs gradient."""
+    in float64 on the same inputs -- for the fp32 kernel AND for the default path (mode None: what `loss.backward()`
+    runs unless told otherwise, i.e. the tcgen05 backward), shared and per-sample embeddings."""
     model, emb = cuda_model
     sd, _ = state_dict
     gen = torch.Generator().manual_seed(21)
@@ -149,6 +157,7 @@ def test_mlp_backward_vs_oracle_autograd(cuda_model, oracle, state_dict):
     x = (torch.rand(s, 3, generator=gen) - 0.5) * 6
     d = torch.nn.functional.normalize(torch.randn(s, 3, generator=gen), dim=-1)
     cot = torch.randn(s, 4, generator=gen)
+    tol, tol_cos = BWD_TOL[mode]
     for rows in (1, s):
         e = torch.randn(rows, 32, generator=gen)
         sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
@@ -157,21 +166,22 @@ def test_mlp_backward_vs_oracle_autograd(cuda_model, oracle, state_dict):
         (torch.cat([rgb, sigma], dim=-1) * cot.double()).sum().backward()
         model.zero_grad()
         eg = e.cuda().requires_grad_(True)
-        model.mlp_mode = "fp32"
+        model.mlp_mode = mode
         try:
             rgb_g, sigma_g = model(x.cuda(), d.cuda(), eg)
         finally:
             model.mlp_mode = None
         (torch.cat([rgb_g, sigma_g], dim=-1) * cot.cuda()).sum().backward()
-        worst = 0.0
+        worst, worst_cos = 0.0, 1.0
         for k, p in model.named_parameters():
             ref = sd64[k].grad
             rel = maxabs(p.grad, ref) / (float(ref.abs().max()) + 1e-12)
-            worst = max(worst, rel)
-            assert rel <= 2e-4, (k, rel, rows)
+            cos = float((p.grad.double().cpu() * ref).sum() / (p.grad.double().norm().cpu() * ref.norm() + 1e-30))
+            worst, worst_cos = max(worst, rel), min(worst_cos, cos)
+            assert rel <= tol and cos >= tol_cos, (k, rel, cos, rows, mode)
         rel_e = maxabs(eg.grad, e64.grad) / (float(e64.grad.abs().max()) + 1e-12)
-        record(f"mlp_bwd_rows{rows}", worst_param_rel=worst, emb_rel=rel_e)
-        assert rel_e <= 2e-4, rel_e
+        record(f"mlp_bwd_vs_oracle_{mode or 'default'}_rows{rows}", worst_param_rel=worst, worst_cos=worst_cos, emb_rel=rel_e)
+        assert rel_e <= tol, rel_e
     model.zero_grad()
 
 
@@ -258,34 +268,6 @@ def test_training_forward_keeps_split_direction_layer(cuda_model, golden):
     assert masks.numel() == 9 * 128 * 8 * 4
 
 
-@pytest.mark.parametrize("mode", ["bf16", "fp16", "bf16x3"])
-def test_cta_pair_forward_kernel_bitwise_equal(cuda_model, monkeypatch, mode):
-    """The opt-in CTA-pair forward kernel (NERFW_FWD_PAIR=1: tcgen05 cta_group::2, M = 256 over two SMs, B split by N,
-    peer-CTA epilogues signalling the leader's mbarriers through the cluster) returns the same bits as the default kernel,
-    including an odd tile count (the pair's second tile past the end) and a ragged last tile."""
-    import nerfw
-    from nerfw import ops
-    model, emb = cuda_model
-    names, tensors = model.kernel_params()
-    params = {k: t.detach() for k, t in zip(names, tensors)}
-    packed = model.packed_weights(names, tensors)
-    mode_id = nerfw.models.resolve_mode(mode)
-    g = torch.Generator(device="cuda").manual_seed(11)
-    for b, n in ((400, 192), (399, 97)):          # 600 tiles; 302.4 -> 303 tiles (odd, ragged)
-        o = torch.randn(b, 3, device="cuda", generator=g)
-        d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda", generator=g), dim=-1)
-        z = torch.sort(torch.rand(b, n, device="cuda", generator=g) * 4 + 2, dim=-1).values
-        monkeypatch.delenv("NERFW_FWD_PAIR", raising=False)
-        want, wmask = ops.mlp_fwd(params, packed, o, d, z, emb.reshape(1, -1), mode_id, want_masks=True)
-        monkeypatch.setenv("NERFW_FWD_PAIR", "1")
-        got, gmask = ops.mlp_fwd(params, packed, o, d, z, emb.reshape(1, -1), mode_id, want_masks=True)
-        monkeypatch.delenv("NERFW_FWD_PAIR")
-        assert torch.equal(got, want)
-        # gate words: [tile][layer 0..8][row][8 words]; the direction layer (8) only writes words 0, 1, 4, 5
-        gm, wm = gmask.view(torch.int32).view(-1, 9, 128, 8), wmask.view(torch.int32).view(-1, 9, 128, 8)
-        assert torch.equal(gm[:, :8], wm[:, :8]) and torch.equal(gm[:, 8][..., [0, 1, 4, 5]], wm[:, 8][..., [0, 1, 4, 5]])
-
-
 @pytest.mark.parametrize("mode", ["bf16x3", "fp16", "bf16"])
 def test_sigma_only_flag(cuda_model, oracle, mode):
     """NERFW_MLP_SIGMA_ONLY: same sigma bits as the full forward, rgb = 0; and the hierarchical render is bit-identical
@@ -310,9 +292,10 @@ def test_sigma_only_flag(cuda_model, oracle, mode):
     oc, dc = ro[40:60, 40:60].reshape(-1, 3), rd[40:60, 40:60].reshape(-1, 3)
     u = torch.rand(400, 128, generator=torch.Generator().manual_seed(2))
     with torch.no_grad():
-        a = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, appearance_embedding=emb, perturb=False, mlp_dtype=mode, u_rand=u)
+        a = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, appearance_embedding=emb, perturb=False, mlp_dtype=mode, u_rand=u,
+                                reuse_coarse=False)
         bb = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, appearance_embedding=emb, perturb=False, mlp_dtype=mode, u_rand=u,
-                                 coarse_rgb=True)
+                                 coarse_rgb=True, reuse_coarse=False)
     assert "rgb_coarse" not in a[2] and "rgb_coarse" in bb[2]
     assert torch.equal(a[0], bb[0]) and torch.equal(a[1], bb[1]) and torch.equal(a[2]["z_vals"], bb[2]["z_vals"])
     assert torch.equal(a[2]["depth_coarse"], bb[2]["depth_coarse"])

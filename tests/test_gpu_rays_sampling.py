@@ -155,9 +155,7 @@ def test_sample_pdf_merge_path_equals_general_path(oracle, monkeypatch):
     z[1700:1800] = z[1700:1800].flip(-1)     # unsorted depths -> fallback
     w[1800:1900, ::7] = -0.5                 # non-monotone cdf -> fallback
     got, aux = ops.sample_pdf(z, w, ni, u, want_aux=True)
-    monkeypatch.setenv("NERFW_RESAMPLE_GENERAL", "1")
-    want, aux_w = ops.sample_pdf(z, w, ni, u, want_aux=True)
-    monkeypatch.delenv("NERFW_RESAMPLE_GENERAL")
+    want, aux_w = ops.sample_pdf(z, w, ni, u, want_aux=True, general_path=True)   # nerfw_sample_pdf_general
     assert torch.equal(got, want)
     assert torch.equal(aux["inds"], aux_w["inds"]) and torch.equal(aux["z_fine"], aux_w["z_fine"])
     # and both equal the oracle where its searchsorted is well defined (sorted cdf)

@@ -40,9 +40,8 @@ def test_view100_coarse_golden(cuda_model, oracle, golden, mode):
     assert e["rgb"] <= t[0] and e["depth"] <= t[1] and e["acc"] <= t[2], e
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
-def test_dense_scene_crop(cuda_model, oracle, golden, state_dict, mode):
-    """density head x200, bias +1: acc ~ 1, the depth-sensitive case (SURVEY.md hard part 3)."""
+def dense_model(state_dict):
+    """density head x200, bias +1 (acc ~ 1, like a trained opaque scene): the variant oracle/make_golden.py renders."""
     import nerfw
     from config import Config
     sd, emb = state_dict
@@ -51,7 +50,25 @@ def test_dense_scene_crop(cuda_model, oracle, golden, state_dict, mode):
     sd["density_head.bias"] += 1.0
     m = nerfw.NeRF(Config())
     m.load_state_dict(sd)
-    m = m.cuda()
+    return m.cuda(), emb.cuda()
+
+
+def index_mismatch_rate(ex, u_rand, want_inds):
+    """End-to-end sample-index mismatch rate: searchsorted indices of the resampling step as the
+    GPU path computed them (its own coarse weights -> cdf -> inds) against the oracle's, same uniforms."""
+    from nerfw import ops
+    w = ex["weights_coarse"].squeeze(-1).contiguous()
+    _, aux = ops.sample_pdf(ex["z_vals_coarse"], w, u_rand.shape[1], u_rand.cuda(), want_aux=True)
+    return float((aux["inds"].cpu() != torch.from_numpy(want_inds).long()).float().mean())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "mixed", "fp16", "bf16"])
+def test_dense_scene_crop(cuda_model, oracle, golden, state_dict, mode):
+    """density head x200, bias +1: acc ~ 1, the depth-sensitive case (SURVEY.md hard part 3).  Single pass: "mixed"
+    resolves to bf16x3; the bars are the same 1x bars as everywhere else."""
+    import nerfw
+    m, emb_d = dense_model(state_dict)
+    _, emb = state_dict
     o, d = view(oracle)
     g = golden("crop20_dense")
     with torch.no_grad():
@@ -60,7 +77,36 @@ def test_dense_scene_crop(cuda_model, oracle, golden, state_dict, mode):
     e = dict(rgb=maxabs(rgb, g["rgb"]), depth=maxabs(depth, g["depth"]), acc=maxabs(ex["acc"], g["acc"]))
     record(f"crop20_dense_{mode}", **e)
     t = TOL[mode]
-    assert e["rgb"] <= t[0] * 3 and e["depth"] <= t[1] * 3 and e["acc"] <= t[2] * 3, e
+    assert e["rgb"] <= t[0] and e["depth"] <= t[1] and e["acc"] <= t[2], e
+
+
+@pytest.mark.parametrize("reuse", [False, True])
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "mixed", "fp16", "bf16"])
+def test_dense_hierarchical_golden(oracle, golden, state_dict, mode, reuse):
+    """The opaque-scene case of the headline path: density x200 (mean acc 0.99), coarse 64 + fine 64+128, fixed uniforms,
+    both the two-pass form and the default reuse_coarse form, against the composed oracle whose coarse half is asserted
+    bit-equal to the reference's own volume_render (oracle/make_golden.py).  1x bars."""
+    import nerfw
+    m, emb = dense_model(state_dict)
+    o, d = view(oracle)
+    g = golden("crop24_dense_hier")
+    oc, dc = o[38:62, 38:62].reshape(-1, 3), d[38:62, 38:62].reshape(-1, 3)
+    u = torch.from_numpy(g["u_rand"])
+    with torch.no_grad():
+        rgb, depth, ex = nerfw.volume_render(m, oc, dc, 2.0, 6.0, 64, 128, appearance_embedding=emb, perturb=False,
+                                             mlp_dtype=mode, u_rand=u, reuse_coarse=reuse)
+    assert ex["z_vals"].shape == (576, 192)
+    de = (depth.cpu() - torch.from_numpy(g["depth"])).abs().reshape(-1)
+    e = dict(rgb=maxabs(rgb, g["rgb"]), depth=float(de.max()), acc=maxabs(ex["acc"], g["acc"]),
+             depth_coarse=maxabs(ex["depth_coarse"], g["depth_coarse"]),
+             w_coarse=maxabs(ex["weights_coarse"].squeeze(-1), g["weights_coarse"]),
+             depth_p99=float(de.kthvalue(int(0.99 * de.numel())).values), rays_over_bar=float((de > 1e-3).sum()),
+             ind_mismatch_rate=index_mismatch_rate(ex, u, g["inds"]), mean_acc=float(ex["acc"].mean()))
+    record(f"crop24_dense_hier_{mode}{'_reuse' if reuse else ''}", **e)
+    t = TOL[mode]
+    assert e["rgb"] <= t[0] and e["depth"] <= t[1] and e["acc"] <= t[2], e
+    if mode in ("fp32", "bf16x3", "mixed"):     # the coarse pass keeps fp32-level weights in these modes
+        assert e["ind_mismatch_rate"] <= 1e-4, e
 
 
 def test_perturbed_render_rng_parity(cuda_model, oracle, golden):
@@ -96,11 +142,17 @@ def test_hierarchical_golden(cuda_model, oracle, golden, mode):
     assert ex["z_vals"].shape == (1024, 192) and ex["weights"].shape == (1024, 192, 1)
     zmis = float((ex["z_vals"].cpu() != torch.from_numpy(g["z_vals"])).float().mean())
     e = dict(rgb=maxabs(rgb, g["rgb"]), depth=maxabs(depth, g["depth"]), acc=maxabs(ex["acc"], g["acc"]),
-             z=maxabs(ex["z_vals"], g["z_vals"]), z_mismatch_rate=zmis)
+             z=maxabs(ex["z_vals"], g["z_vals"]), z_mismatch_rate=zmis,
+             ind_mismatch_rate=index_mismatch_rate(ex, torch.from_numpy(g["u_rand"]), g["inds"]))
     record(f"crop32_hier_{mode}", **e)
     t = TOL[mode]
     assert e["rgb"] <= t[0] and e["depth"] <= t[1] and e["acc"] <= t[2], e
     assert bool((ex["z_vals"][:, 1:] >= ex["z_vals"][:, :-1]).all())
+    if mode in ("fp32", "bf16x3", "mixed"):
+        # north star: "sample indices for fixed seeds, bit-exact" holds given identical cdf / u (tests/
+        # test_gpu_rays_sampling.py); end to end the cdf carries the coarse weights' last-bit differences, which flip an
+        # index only when a u lands within ~1e-7 of a cdf entry (expected <= 1e-5)
+        assert e["ind_mismatch_rate"] <= 1e-4, e
 
 
 def test_chunked_equals_whole_and_cpu_inputs(cuda_model, oracle):
@@ -123,9 +175,12 @@ def test_chunked_equals_whole_and_cpu_inputs(cuda_model, oracle):
     assert empty[0].shape == (0, 3) and empty[1].shape == (0, 1)
 
 
-def test_training_gradients_golden(cuda_model, oracle, golden, manifest):
+@pytest.mark.parametrize("mode", ["fp32", None])
+def test_training_gradients_golden(cuda_model, oracle, golden, manifest, mode):
     """loss.backward() through volume_render (src/train.py:77-91) on 64 rays: loss, embedding gradient, every bias /
-    head gradient stored in the golden file, and all 24 gradient norms, vs autograd through the reference."""
+    head gradient stored in the golden file, and all 24 gradient norms, vs autograd through the REFERENCE -- in the fp32
+    mode and in the default mode (None: bf16x3 forward + tcgen05 bf16 backward, what a training script gets).
+    Bounds: fp32 5e-4 of each tensor's max gradient, norms 1e-3, loss 1e-6; default 3e-2 / 1e-2 / 1e-5."""
     import nerfw
     model, emb = cuda_model
     o, d = view(oracle)
@@ -135,24 +190,26 @@ def test_training_gradients_golden(cuda_model, oracle, golden, manifest):
     t_rand = torch.rand(64, 64)
     emb_p = emb.clone().requires_grad_(True)
     model.zero_grad()
+    tol, tol_norm, tol_loss = (5e-4, 1e-3, 1e-6) if mode == "fp32" else (3e-2, 1e-2, 1e-5)
     rgb, _, _ = nerfw.volume_render(model, o.reshape(-1, 3)[sel], d.reshape(-1, 3)[sel], 2.0, 6.0, 64, 0,
-                                    appearance_embedding=emb_p, perturb=True, mlp_dtype="fp32", t_rand=t_rand)
+                                    appearance_embedding=emb_p, perturb=True, mlp_dtype=mode, t_rand=t_rand)
     loss = torch.nn.functional.mse_loss(rgb, torch.from_numpy(g["target"]).cuda())
     loss.backward()
-    assert abs(float(loss) - float(g["loss"])) <= 1e-6
-    worst = 0.0
+    assert abs(float(loss) - float(g["loss"])) <= tol_loss
+    worst, worst_norm = 0.0, 0.0
     for k, p in model.named_parameters():
         key = k.replace(".", "__")
         ref_norm = manifest["cases"]["grads_64"]["grad_norms"][k]
         rel_n = abs(float(p.grad.double().norm()) - ref_norm) / (ref_norm + 1e-12)
-        assert rel_n <= 1e-3, (k, rel_n)
+        worst_norm = max(worst_norm, rel_n)
+        assert rel_n <= tol_norm, (k, rel_n)
         if key in g.files:
             rel = maxabs(p.grad, g[key]) / (float(np.abs(g[key]).max()) + 1e-12)
             worst = max(worst, rel)
-            assert rel <= 5e-4, (k, rel)
+            assert rel <= tol, (k, rel)
     rel_e = maxabs(emb_p.grad, g["emb_grad"]) / (float(np.abs(g["emb_grad"]).max()) + 1e-12)
-    record("train_grads_64", worst_rel=worst, emb_rel=rel_e, loss=float(loss))
-    assert rel_e <= 5e-4
+    record(f"train_grads_64_{mode or 'default'}", worst_rel=worst, worst_norm_rel=worst_norm, emb_rel=rel_e, loss=float(loss))
+    assert rel_e <= tol
     model.zero_grad()
 
 
@@ -209,7 +266,7 @@ def test_ray_bank_checkpoint_and_fog(cuda_model, oracle, tmp_path):
     table = torch.nn.Parameter(torch.randn(3, 32))
     path = save_checkpoint(str(tmp_path), 1000, model, table, loss=0.5, psnr=3.0)
     assert path.endswith("checkpoint_001000.pt")
-    ck = torch.load(path, weights_only=False)
+    ck = torch.load(path, weights_only=True)
     assert set(ck) == {"model_state_dict", "optimizer_state_dict", "loss", "psnr", "iteration", "appearance_embeddings"}
     m2 = nerfw.NeRF(Config())
     t2 = torch.nn.Parameter(torch.zeros(3, 32))
@@ -302,9 +359,9 @@ def test_odd_sample_counts_end_to_end(cuda_model, oracle, state_dict, n, ni):
     assert e["rgb"] <= 1e-3 and e["depth"] <= 2e-3 and e["acc"] <= 1e-3, e
 
 
-def test_reuse_coarse_opt_in(cuda_model, oracle, golden):
-    """reuse_coarse=True (one network for both passes, inference): the fine pass evaluates only the 128 new samples and the
-    coarse outputs are merged in by depth.  In bf16x3 mode every sample is evaluated by the same kernel either way, so the
+def test_reuse_coarse_equals_two_pass(cuda_model, oracle, golden):
+    """reuse_coarse (the inference default with one network for both passes): the fine pass evaluates only the 128 new
+    samples and the coarse outputs are merged in by depth.  In bf16x3 mode every sample is evaluated by the same kernel either way, so the
     result is bit-identical to the default path; in the default mixed mode it stays inside the fp32 parity bars."""
     import nerfw
     model, emb = cuda_model
@@ -315,8 +372,8 @@ def test_reuse_coarse_opt_in(cuda_model, oracle, golden):
     u = torch.from_numpy(g["u_rand"])
     kw = dict(appearance_embedding=emb, perturb=False, u_rand=u)
     with torch.no_grad():
-        ref = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", **kw)
-        got = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", reuse_coarse=True, **kw)
+        ref = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", reuse_coarse=False, **kw)
+        got = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", **kw)   # default: reuse
         assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and torch.equal(got[2]["weights"], ref[2]["weights"])
         assert torch.equal(got[2]["z_vals"], ref[2]["z_vals"])
         mix = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="mixed", reuse_coarse=True, **kw)
@@ -327,6 +384,21 @@ def test_reuse_coarse_opt_in(cuda_model, oracle, golden):
         u_bad = u.clone()
         u_bad[:64] *= 3.0
         kw_bad = dict(appearance_embedding=emb, perturb=False, u_rand=u_bad)
-        ref_b = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", **kw_bad)
+        ref_b = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", reuse_coarse=False, **kw_bad)
         got_b = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", reuse_coarse=True, **kw_bad)
         assert torch.equal(got_b[0], ref_b[0]) and torch.equal(got_b[1], ref_b[1])
+        # fp32 CUDA-core mode: same property; and a (coarse, fine) pair or a recorded graph never takes the reuse path
+        r32 = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="fp32", reuse_coarse=False, **kw)
+        g32 = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="fp32", **kw)
+        assert torch.equal(g32[0], r32[0]) and torch.equal(g32[1], r32[1])
+        pair = nerfw.volume_render((model, model), oc, dc, 2.0, 6.0, 64, 128, mlp_dtype="bf16x3", **kw)
+        assert torch.equal(pair[0], ref[0])
+    # N + NI = 4096: the merge kernel's 64 KB of dynamic shared memory (above the 48 KB default limit)
+    with torch.no_grad():
+        ub = torch.rand(8, 3584, generator=torch.Generator().manual_seed(3))
+        big = nerfw.volume_render(model, oc[:8], dc[:8], 2.0, 6.0, 512, 3584, appearance_embedding=emb, perturb=False,
+                                  mlp_dtype="bf16x3", u_rand=ub)
+        big2 = nerfw.volume_render(model, oc[:8], dc[:8], 2.0, 6.0, 512, 3584, appearance_embedding=emb, perturb=False,
+                                   mlp_dtype="bf16x3", u_rand=ub, reuse_coarse=False)
+    assert big[2]["z_vals"].shape == (8, 4096) and bool(torch.isfinite(big[0]).all())
+    assert torch.equal(big[0], big2[0]) and torch.equal(big[1], big2[1])

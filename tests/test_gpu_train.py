@@ -110,3 +110,87 @@ def test_loss_decreases_coarse_and_fine(state_dict, oracle, mode):
     record(f"train_loss_{mode}", first=losses[0], last=losses[-1])
     assert losses[-1] < losses[0] * 0.9, losses
     assert all(torch.isfinite(p).all() for p in m.parameters())
+
+
+def _twin(sd, mode, table_seed=4):
+    import nerfw
+    from config import Config
+    from nerfw.train import Trainer
+    m = nerfw.NeRF(Config())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    torch.manual_seed(table_seed)
+    table = torch.nn.Parameter(torch.randn(5, 32, device="cuda"))
+    return m, table, Trainer(m, table, lr=5e-4, mlp_dtype=mode)
+
+
+def test_trainer_default_mode_tracks_fp32(state_dict, oracle):
+    """The DEFAULT training arithmetic ("mixed": bf16x3 coarse + fp16 fine forward, tcgen05 bf16 backward) against the
+    fp32 CUDA-core path on the same batches and jitter: per-step losses within 2e-4 relative, first-step gradients within
+    the stated bf16 bound (3e-2 of each tensor's max, cosine >= 0.999), parameters after 8 Adam steps within 8 lr."""
+    import nerfw
+    sd, _ = state_dict
+    h, w, focal, c2w = oracle.golden_camera()
+    o, d = nerfw.get_rays(h, w, focal, c2w.cuda())
+    sel = torch.arange(0, 10000, 19, device="cuda")[:512]
+    o, d = o.reshape(-1, 3)[sel].contiguous(), d.reshape(-1, 3)[sel].contiguous()
+    tgt = torch.rand(512, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    ma, ta, tra = _twin(sd, None)        # default
+    mb, tb, trb = _twin(sd, "fp32")
+    worst_loss = 0.0
+    for step in range(8):
+        torch.manual_seed(200 + step)
+        la = float(tra.step(o, d, tgt, 3, 2.0, 6.0, 64, 128, perturb=True))
+        torch.manual_seed(200 + step)
+        lb = float(trb.step(o, d, tgt, 3, 2.0, 6.0, 64, 128, perturb=True))
+        worst_loss = max(worst_loss, abs(la - lb) / lb)
+        if step == 0:
+            worst, worst_cos = 0.0, 1.0
+            for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+                ga, gb = pa.grad.double(), pb.grad.double()
+                rel = float((ga - gb).abs().max() / (gb.abs().max() + 1e-20))
+                cos = float((ga * gb).sum() / (ga.norm() * gb.norm() + 1e-30))
+                worst, worst_cos = max(worst, rel), min(worst_cos, cos)
+                assert rel <= 3e-2 and cos >= 0.999, (k, rel, cos)
+    diffs = torch.cat([(pa - pb).abs().reshape(-1) for (_, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters())])
+    record("trainer_default_vs_fp32", worst_loss_rel=worst_loss, grad_rel=worst, grad_cos=worst_cos,
+           param_abs=float(diffs.max()), param_mean_abs=float(diffs.mean()))
+    assert worst_loss <= 2e-4, worst_loss
+    assert float(diffs.max()) <= 8 * 2 * 5e-4     # Adam moves every element by <= ~lr per step
+    assert float((ta - tb).abs().max()) <= 8 * 2 * 5e-4 and float(ta[0].sub(tb[0]).abs().max()) == 0.0
+
+
+def test_checkpoint_resume_keeps_training(state_dict, oracle, tmp_path):
+    """save -> load into a live Trainer: parameters are copied IN PLACE (the flat-buffer views stay attached, so training
+    continues to move the tensors the forward reads), Adam moments and step count come back, and the resumed run
+    reproduces the uninterrupted one bit for bit (fp32 mode, same jitter)."""
+    import nerfw
+    from nerfw.checkpoint import load_checkpoint, save_checkpoint
+    sd, _ = state_dict
+    h, w, focal, c2w = oracle.golden_camera()
+    o, d = nerfw.get_rays(h, w, focal, c2w.cuda())
+    sel = torch.arange(0, 10000, 79, device="cuda")[:128]
+    o, d = o.reshape(-1, 3)[sel].contiguous(), d.reshape(-1, 3)[sel].contiguous()
+    tgt = torch.full((128, 3), 0.7, device="cuda")
+
+    def run(tr, steps, first):
+        for s in range(first, first + steps):
+            torch.manual_seed(300 + s)
+            tr.step(o, d, tgt, 1, 2.0, 6.0, 64, 0, perturb=True)
+
+    ma, ta, tra = _twin(sd, "fp32")
+    run(tra, 3, 0)
+    path = save_checkpoint(str(tmp_path), 3, ma, ta, optimizer_state=tra.state_dict(), loss=0.1, psnr=10.0)
+    run(tra, 2, 3)                                   # the uninterrupted run: 5 steps
+    mb, tb, trb = _twin(sd, "fp32", table_seed=9)    # a fresh process would start from other values
+    ptr_before = mb.rgb_linear.weight.data_ptr()
+    ck = load_checkpoint(path, mb, tb, trainer=trb)
+    assert ck["iteration"] == 3 and trb.step_count == 3
+    assert mb.rgb_linear.weight.data_ptr() == ptr_before                       # still a view of the flat buffer
+    assert tb.data_ptr() == trb.flat.param.data_ptr() + trb.flat.offsets[-2] * 4
+    run(trb, 2, 3)
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert maxabs(pa, pb) <= 2e-6, k              # atomics order in the backward only
+    assert maxabs(ta, tb) <= 2e-6
+    with pytest.raises(RuntimeError, match="shape"):
+        load_checkpoint(path, mb, torch.nn.Parameter(torch.zeros(4, 32, device="cuda")))
