@@ -254,10 +254,26 @@ __global__ void __launch_bounds__(CP_WARPS * 32) composite_bwd_reg_kernel(
 // immaterial).  One warp per ray, both depth lists in shared memory, fixed-length binary searches.  Used by the opt-in
 // `reuse_coarse` path of volume_render: when coarse and fine pass share one network, the fine pass only has to evaluate
 // the NI new samples instead of all N + NI.
+//
+// BACK = true is the transpose (the backward of the merge): the gradient of the merged row is scattered back to the two
+// lists -- d_fine[k] = d_merged[slot(k)], d_coarse[i] (+)= d_merged[slot(i)] (ACC: the coarse list already holds the
+// gradient that arrived through the coarse pass's own outputs).  Same slot computation, so forward and backward agree.
 constexpr int MG_WARPS = 4;
-__global__ void __launch_bounds__(MG_WARPS * 32) merge_raw_kernel(const float* __restrict__ zc, const float4* __restrict__ rc,
-                                                                  const float* __restrict__ zf, const float4* __restrict__ rf,
+template <bool BACK, bool ACC>
+__global__ void __launch_bounds__(MG_WARPS * 32) merge_raw_kernel(const float* __restrict__ zc, float4* __restrict__ rc,
+                                                                  const float* __restrict__ zf, float4* __restrict__ rf,
                                                                   int64_t B, int N, int NI, float4* __restrict__ out) {
+  // one (record, slot) pair: forward copies list -> merged row, backward merged row -> list
+  auto move_c = [&](int64_t ray, int i, float4* o, int slot) {
+    if (!BACK) { o[slot] = __ldg(rc + ray * N + i); return; }
+    float4 g = o[slot];
+    if (ACC) { const float4 a = rc[ray * N + i]; g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
+    rc[ray * N + i] = g;
+  };
+  auto move_f = [&](int64_t ray, int k, float4* o, int slot) {
+    if (!BACK) o[slot] = __ldg(rf + ray * NI + k);
+    else rf[ray * NI + k] = o[slot];
+  };
   extern __shared__ float mg_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sc = mg_smem + (size_t)warp * (N + NI);
@@ -281,7 +297,7 @@ __global__ void __launch_bounds__(MG_WARPS * 32) merge_raw_kernel(const float* _
           const float w = j < N ? sc[j] : sf[j - N];
           rank += (w < v || (w == v && j < e)) ? 1 : 0;
         }
-        o[rank] = is_c ? __ldg(rc + ray * N + e) : __ldg(rf + ray * NI + (e - N));
+        if (is_c) move_c(ray, e, o, rank); else move_f(ray, e - N, o, rank);
       }
       __syncwarp();
       continue;
@@ -290,13 +306,13 @@ __global__ void __launch_bounds__(MG_WARPS * 32) merge_raw_kernel(const float* _
       const float v = sc[i];
       int lo = 0, hi = NI;
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (sf[mid] < v) lo = mid + 1; else hi = mid; }
-      o[i + lo] = __ldg(rc + ray * N + i);
+      move_c(ray, i, o, i + lo);
     }
     for (int k = lane; k < NI; k += 32) {         // #{i : z_i <= zf_k}: upper bound in the coarse list
       const float v = sf[k];
       int lo = 0, hi = N;
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (sc[mid] <= v) lo = mid + 1; else hi = mid; }
-      o[k + lo] = __ldg(rf + ray * NI + k);
+      move_f(ray, k, o, k + lo);
     }
     __syncwarp();
   }
@@ -347,22 +363,43 @@ extern "C" int nerfw_composite_bwd(const float* raw, const float* z, int64_t n_r
   return NERFW_OK;
 }
 
-extern "C" int nerfw_merge_raw(const float* z_coarse, const float* raw_coarse, const float* z_fine, const float* raw_fine,
-                               int64_t n_rays, int n_samples, int n_importance, float* raw_out, void* stream) {
+static int merge_launch(const char* who, const float* z_coarse, float* raw_coarse, const float* z_fine, float* raw_fine,
+                        int64_t n_rays, int n_samples, int n_importance, float* merged, int back, int acc, void* stream) {
   NERFW_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_importance >= 1 && n_samples + n_importance <= 4096,
-                "nerfw_merge_raw: bad shape B=%lld N=%d NI=%d", (long long)n_rays, n_samples, n_importance);
+                "%s: bad shape B=%lld N=%d NI=%d", who, (long long)n_rays, n_samples, n_importance);
   if (n_rays == 0) return NERFW_OK;
-  NERFW_REQUIRE(z_coarse && raw_coarse && z_fine && raw_fine && raw_out, "nerfw_merge_raw: null pointer");
-  NERFW_REQUIRE(aligned16(raw_coarse) && aligned16(raw_fine) && aligned16(raw_out), "nerfw_merge_raw: raw buffers must be 16-byte aligned");
+  NERFW_REQUIRE(z_coarse && raw_coarse && z_fine && raw_fine && merged, "%s: null pointer", who);
+  NERFW_REQUIRE(aligned16(raw_coarse) && aligned16(raw_fine) && aligned16(merged), "%s: record buffers must be 16-byte aligned", who);
   const size_t smem = (size_t)MG_WARPS * (n_samples + n_importance) * sizeof(float);
-  if (smem > 48 * 1024)   // up to 64 KB at N + NI = 4096
-    NERFW_CUDA(cudaFuncSetAttribute(merge_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = ceil_div64(n_rays, MG_WARPS);
   const int64_t cap = (int64_t)sm_count() * 32;
   if (blocks > cap) blocks = cap;
-  merge_raw_kernel<<<(unsigned)blocks, MG_WARPS * 32, smem, as_stream(stream)>>>(
-      z_coarse, reinterpret_cast<const float4*>(raw_coarse), z_fine, reinterpret_cast<const float4*>(raw_fine), n_rays,
-      n_samples, n_importance, reinterpret_cast<float4*>(raw_out));
+  auto launch = [&](auto kernel) -> int {
+    if (smem > 48 * 1024)   // up to 64 KB at N + NI = 4096
+      NERFW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)blocks, MG_WARPS * 32, smem, as_stream(stream)>>>(
+        z_coarse, reinterpret_cast<float4*>(raw_coarse), z_fine, reinterpret_cast<float4*>(raw_fine), n_rays, n_samples,
+        n_importance, reinterpret_cast<float4*>(merged));
+    return NERFW_OK;
+  };
+  int rc;
+  if (!back) rc = launch(merge_raw_kernel<false, false>);
+  else if (acc) rc = launch(merge_raw_kernel<true, true>);
+  else rc = launch(merge_raw_kernel<true, false>);
+  if (rc != NERFW_OK) return rc;
   NERFW_LAUNCHED();
   return NERFW_OK;
+}
+
+extern "C" int nerfw_merge_raw(const float* z_coarse, const float* raw_coarse, const float* z_fine, const float* raw_fine,
+                               int64_t n_rays, int n_samples, int n_importance, float* raw_out, void* stream) {
+  return merge_launch("nerfw_merge_raw", z_coarse, const_cast<float*>(raw_coarse), z_fine, const_cast<float*>(raw_fine), n_rays,
+                      n_samples, n_importance, raw_out, 0, 0, stream);
+}
+
+extern "C" int nerfw_unmerge_raw(const float* z_coarse, const float* z_fine, const float* d_raw_merged, int64_t n_rays,
+                                 int n_samples, int n_importance, int accumulate_coarse, float* d_raw_coarse,
+                                 float* d_raw_fine, void* stream) {
+  return merge_launch("nerfw_unmerge_raw", z_coarse, d_raw_coarse, z_fine, d_raw_fine, n_rays, n_samples, n_importance,
+                      const_cast<float*>(d_raw_merged), 1, accumulate_coarse ? 1 : 0, stream);
 }

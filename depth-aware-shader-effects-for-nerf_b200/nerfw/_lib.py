@@ -75,6 +75,8 @@ SIGNATURES = {
     "nerfw_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nerfw_quantize_u8": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nerfw_merge_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nerfw_unmerge_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "nerfw_max_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nerfw_fog": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                             C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),

@@ -166,6 +166,21 @@ def merge_raw(z_coarse: torch.Tensor, raw_coarse: torch.Tensor, z_fine: torch.Te
     return out
 
 
+def unmerge_raw(z_coarse: torch.Tensor, z_fine: torch.Tensor, d_merged: torch.Tensor,
+                d_coarse: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Backward of merge_raw: d_merged (B*(N+NI),4) -> (d_coarse (B*N,4), d_fine (B*NI,4)).  A given d_coarse is added to."""
+    b, n = z_coarse.shape
+    ni = z_fine.shape[1]
+    acc = d_coarse is not None
+    if d_coarse is None:
+        d_coarse = torch.empty((b * n, 4), dtype=torch.float32, device=z_coarse.device)
+    d_fine = torch.empty((b * ni, 4), dtype=torch.float32, device=z_coarse.device)
+    with torch.cuda.device(z_coarse.device):
+        check(lib().nerfw_unmerge_raw(z_coarse.data_ptr(), z_fine.data_ptr(), _f32c(d_merged, "d_merged").data_ptr(), b, n, ni,
+                                      int(acc), d_coarse.data_ptr(), d_fine.data_ptr(), _stream()))
+    return d_coarse, d_fine
+
+
 def posenc(x: torch.Tensor, levels: int, include_input: bool = True) -> torch.Tensor:
     x = _f32c(x, "x")
     dim = x.shape[-1]

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from .autograd import RenderFn
+from .autograd import RenderFn, ReuseRenderFn
 from .models import NeRF, resolve_mode
 
 
@@ -30,19 +30,25 @@ def _shade(model: NeRF, o, d, z, emb, mode, role="single", sigma_only=False):
 
 
 def _render_reusing_coarse(model: NeRF, o, d, z, emb, mode, n_importance, u_rand, generator, orig_shape, src_dev):
-    """Hierarchical inference render with one network: coarse pass on z (full outputs), resampling, fine pass on the NEW
-    depths only, merge of both sets of (r,g,b,sigma) records into depth order, compositing of the merged row."""
+    """Hierarchical render with one network: coarse pass on z (full outputs), resampling, fine pass on the NEW depths
+    only, merge of both sets of (r,g,b,sigma) records into depth order, compositing of the merged row.  Differentiable
+    (ReuseRenderFn) when gradients are being recorded."""
     dev, b = o.device, o.shape[0]
-    params = model.kernel_state()[2]
-    packed = model.packed_weights()
-    e = None if emb is None else emb.detach()
-    raw_c = ops.mlp_fwd(params, packed, o, d, z, e, resolve_mode(mode or model.mlp_mode, "coarse"))
-    rgb_c, depth_c, acc_c, w_c = ops.composite_fwd(raw_c, z, want_weights=True)
+    names, tensors, params = model.kernel_state()[:3]
+    mode_c, mode_f = resolve_mode(mode or model.mlp_mode, "coarse"), resolve_mode(mode or model.mlp_mode, "fine")
+    packed = model.packed_weights() if (mode_c != 0 or mode_f != 0) else None
     ur = u_rand.to(dev).reshape(b, n_importance) if u_rand is not None else torch.rand((b, n_importance), device=dev, generator=generator)
-    z_all, z_new = ops.sample_pdf(z, w_c, n_importance, ur, want_zfine=True)       # src/ray_utils.py:90-149
-    raw_f = ops.mlp_fwd(params, packed, o, d, z_new, e, resolve_mode(mode or model.mlp_mode, "fine"))
-    raw = ops.merge_raw(z, raw_c, z_new, raw_f)
-    rgb, depth, acc, w = ops.composite_fwd(raw, z_all, want_weights=True)
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or (emb is not None and emb.requires_grad)):
+        rgb, depth, acc, w, rgb_c, depth_c, acc_c, w_c, z_all = ReuseRenderFn.apply(mode_c, mode_f, names, o, d, z, emb, packed,
+                                                                                   ur.float().contiguous(), *tensors)
+    else:
+        e = None if emb is None else emb.detach()
+        raw_c = ops.mlp_fwd(params, packed, o, d, z, e, mode_c)
+        rgb_c, depth_c, acc_c, w_c = ops.composite_fwd(raw_c, z, want_weights=True)
+        z_all, z_new = ops.sample_pdf(z, w_c, n_importance, ur, want_zfine=True)       # src/ray_utils.py:90-149
+        raw_f = ops.mlp_fwd(params, packed, o, d, z_new, e, mode_f)
+        raw = ops.merge_raw(z, raw_c, z_new, raw_f)
+        rgb, depth, acc, w = ops.composite_fwd(raw, z_all, want_weights=True)
     extras = {"rgb_coarse": rgb_c.reshape(*orig_shape[:-1], 3), "depth_coarse": depth_c.reshape(*orig_shape[:-1], 1),
               "acc_coarse": acc_c, "weights_coarse": w_c.unsqueeze(-1), "z_vals_coarse": z,
               "weights": w.unsqueeze(-1), "z_vals": z_all, "acc": acc}
@@ -70,8 +76,10 @@ def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
     depend on which pass asks, so the fine pass evaluates only the n_importance NEW depths and the coarse pass's
     (r,g,b,sigma) records are merged in at the n_samples coarse depths: 192 instead of 256 MLP evaluations per ray at
     64 + 128.  Bit-identical to the two-pass form in fp32 / bf16x3; in "mixed" the coarse records keep their bf16x3
-    values (closer to fp32 than the fp16 re-evaluation they replace).  Training (gradients enabled) and (coarse, fine)
-    pairs always evaluate every depth in the fine pass."""
+    values (closer to fp32 than the fp16 re-evaluation they replace).  Under autograd the same holds for the backward
+    (ReuseRenderFn: every depth goes through the MLP backward once; the gradients equal the two-pass form's, where the
+    coarse depths are evaluated twice and the two contributions summed).  (coarse, fine) pairs always evaluate every
+    depth in the fine pass."""
     coarse, fine = (model if isinstance(model, (tuple, list)) else (model, model))
     if fine_pass is None:
         fine_pass = os.environ.get("NERFW_COARSE_ONLY", "0") != "1"
@@ -95,7 +103,7 @@ def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
         coarse_rgb = torch.is_grad_enabled()
     if reuse_coarse is None:
         reuse_coarse = os.environ.get("NERFW_REUSE_COARSE", "1") != "0"
-    reuse_coarse = bool(reuse_coarse) and hier and coarse is fine and not torch.is_grad_enabled()
+    reuse_coarse = bool(reuse_coarse) and hier and coarse is fine
     if reuse_coarse:
         return _render_reusing_coarse(coarse, o, d, z, emb, mlp_dtype, int(n_importance), u_rand, generator, orig_shape, src_dev)
     sigma_only = hier and not coarse_rgb and not torch.is_grad_enabled()

@@ -172,12 +172,19 @@ int nerfw_mlp_bwd_tc(const NerfwWeights* w, const void* packed, const float* pts
                      const void* relu_masks, const NerfwGrads* grads, float* d_emb, void* workspace, size_t workspace_bytes,
                      void* stream);
 
-/* Opt-in shortcut of the hierarchical render when the coarse and the fine pass use ONE network (the reference has a
+/* Shortcut of the hierarchical render when the coarse and the fine pass use ONE network (the reference has a
  * single model, src/render.py:49): the N coarse samples were evaluated in the coarse pass, so the fine pass evaluates only
  * the NI new depths (z_fine of nerfw_sample_pdf) and this call merges both sets of (r,g,b,sigma) records into the depth
  * order of the merged row (src/ray_utils.py:142-144).  raw_out (n_rays, N+NI, 4). */
 int nerfw_merge_raw(const float* z_coarse, const float* raw_coarse, const float* z_fine, const float* raw_fine,
                     int64_t n_rays, int n_samples, int n_importance, float* raw_out, void* stream);
+/* Backward of nerfw_merge_raw (training with one network, so that the fine pass of a training step also evaluates only the
+ * NI new depths): scatters the gradient of the merged records back to the two lists with the same slot computation --
+ * d_raw_fine[k] = d_merged[slot(k)]; d_raw_coarse[i] = d_merged[slot(i)], or += when accumulate_coarse != 0 (the buffer
+ * then already holds the gradient that reached the coarse records through the coarse pass's own outputs). */
+int nerfw_unmerge_raw(const float* z_coarse, const float* z_fine, const float* d_raw_merged, int64_t n_rays,
+                      int n_samples, int n_importance, int accumulate_coarse, float* d_raw_coarse, float* d_raw_fine,
+                      void* stream);
 
 /* ---- compositing: the tail of volume_render -- src/render.py:56-80 ------------------------------------
  * raw (B,N,4) = (r,g,b,sigma), z (B,N).  Out: rgb_map (B,3), depth (B,1), acc (B,1) = sum of weights

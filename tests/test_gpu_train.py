@@ -194,3 +194,101 @@ def test_checkpoint_resume_keeps_training(state_dict, oracle, tmp_path):
     assert maxabs(ta, tb) <= 2e-6
     with pytest.raises(RuntimeError, match="shape"):
         load_checkpoint(path, mb, torch.nn.Parameter(torch.zeros(4, 32, device="cuda")))
+
+
+def test_unmerge_is_the_transpose_of_merge():
+    """nerfw_unmerge_raw scatters a merged row back to its two source lists with the slots nerfw_merge_raw used: the round
+    trip is the identity (ties between the lists and an unsorted fine list included), and the accumulate form adds."""
+    from nerfw import ops
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for b, n, ni in ((257, 64, 128), (33, 37, 53), (5, 512, 3584)):
+        zc = torch.sort(torch.rand(b, n, device="cuda", generator=g) * 4 + 2, dim=-1).values
+        zf = torch.sort(torch.rand(b, ni, device="cuda", generator=g) * 4 + 2, dim=-1).values
+        zf[: b // 3, : min(ni, n) // 2] = zc[: b // 3, : min(ni, n) // 2]          # exact ties between the two lists
+        zf[b // 3: b // 2] = zf[b // 3: b // 2].flip(-1)                            # unsorted fine rows: counting fallback
+        rc = torch.randn(b * n, 4, device="cuda", generator=g)
+        rf = torch.randn(b * ni, 4, device="cuda", generator=g)
+        merged = ops.merge_raw(zc, rc, zf, rf)
+        back_c, back_f = ops.unmerge_raw(zc, zf, merged)
+        assert torch.equal(back_c, rc) and torch.equal(back_f, rf), (b, n, ni)
+        base = torch.randn(b * n, 4, device="cuda", generator=g)
+        acc_c, _ = ops.unmerge_raw(zc, zf, merged, base.clone())
+        assert torch.equal(acc_c, base + rc)
+        # the merged depths are sorted wherever both inputs were
+        zm = ops.merge_raw(zc, zc.reshape(-1, 1).expand(-1, 4).contiguous(), zf, zf.reshape(-1, 1).expand(-1, 4).contiguous())[:, 0].reshape(b, n + ni)
+        ok_rows = torch.ones(b, dtype=torch.bool, device="cuda")
+        ok_rows[b // 3: b // 2] = False
+        assert bool((zm[ok_rows][:, 1:] >= zm[ok_rows][:, :-1]).all())
+
+
+@pytest.mark.parametrize("mode", ["fp32", None])
+def test_reuse_coarse_training_gradients_equal_two_pass(cuda_model, oracle, mode):
+    """Training with one network: the default (every depth through the MLP once, ReuseRenderFn) against the two-pass form
+    (coarse depths evaluated in both passes) on a loss that uses the fine AND the coarse outputs.  fp32 mode: the forward
+    is bit-identical and the gradients agree to summation order (1e-4 of each tensor's max); default tensor-core mode:
+    inside the stated bf16 bound (3e-2, cosine >= 0.999)."""
+    import nerfw
+    model, emb = cuda_model
+    h, w, focal, c2w = oracle.golden_camera()
+    o, d = nerfw.get_rays(h, w, focal, c2w.cuda())
+    sel = torch.arange(0, 10000, 23, device="cuda")[:400]
+    o, d = o.reshape(-1, 3)[sel].contiguous(), d.reshape(-1, 3)[sel].contiguous()
+    gen = torch.Generator().manual_seed(12)
+    t_rand, u_rand = torch.rand(400, 64, generator=gen), torch.rand(400, 128, generator=gen)
+    tgt = torch.rand(400, 3, generator=gen).cuda()
+    grads, outs = [], []
+    for reuse in (True, False):
+        model.zero_grad()
+        e = emb.clone().requires_grad_(True)
+        rgb, depth, ex = nerfw.volume_render(model, o, d, 2.0, 6.0, 64, 128, appearance_embedding=e, perturb=True, mlp_dtype=mode,
+                                             t_rand=t_rand, u_rand=u_rand, reuse_coarse=reuse)
+        loss = ((rgb - tgt) ** 2).mean() + ((ex["rgb_coarse"] - tgt) ** 2).mean() + 0.1 * depth.mean() + 0.05 * ex["weights"].sum(1).mean()
+        loss.backward()
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters()} | {"emb": e.grad.clone()})
+        outs.append((rgb.detach(), depth.detach(), ex["z_vals"], float(loss)))
+    if mode == "fp32":
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    tol, tol_cos = (1e-4, 0.999999) if mode == "fp32" else (3e-2, 0.999)
+    worst, worst_cos = 0.0, 1.0
+    for k in grads[0]:
+        a, b_ = grads[0][k].double(), grads[1][k].double()
+        rel = float((a - b_).abs().max() / (b_.abs().max() + 1e-20))
+        cos = float((a * b_).sum() / (a.norm() * b_.norm() + 1e-30))
+        worst, worst_cos = max(worst, rel), min(worst_cos, cos)
+        assert rel <= tol and cos >= tol_cos, (k, rel, cos)
+    record(f"reuse_training_vs_two_pass_{mode or 'default'}", worst_rel=worst, worst_cos=worst_cos, loss_reuse=outs[0][3], loss_two_pass=outs[1][3])
+    model.zero_grad()
+
+
+def test_cross_image_batches_per_ray_embeddings(state_dict, oracle):
+    """RayBank.sample(cross_image=True) draws (image, pixel) pairs over the whole bank and the step gathers
+    one embedding row per ray; the default tensor-core path (per-ray rows in the tcgen05 backward) tracks the fp32 path."""
+    import nerfw
+    from nerfw.camera import aligned_spiral_poses, blender_focal
+    from nerfw.raybank import RayBank
+    sd, _ = state_dict
+    poses = torch.from_numpy(aligned_spiral_poses(6, 1))
+    imgs = torch.rand(6, 24, 32, 3, generator=torch.Generator().manual_seed(2))
+    bank = RayBank(imgs, poses, blender_focal(32))
+    batch = bank.sample(512, generator=torch.Generator(device="cuda").manual_seed(5), cross_image=True)
+    idx = batch["appearance_idx"]
+    assert idx.shape == (512,) and idx.dtype == torch.int64 and len(torch.unique(idx)) > 1
+    flat = idx * (24 * 32)
+    assert torch.equal(batch["rays_o"], bank.origins[idx])
+    pix = torch.stack([(bank.dirs[i] == batch["rays_d"][k]).all(-1).nonzero()[0, 0] for k, i in enumerate(idx.tolist())])
+    assert torch.equal(batch["rgb"], bank.rgb[idx, pix])
+    ma, ta, tra = _twin(sd, None)
+    mb, tb, trb = _twin(sd, "fp32")
+    for step in range(2):
+        torch.manual_seed(400 + step)
+        la = float(tra.step(batch["rays_o"], batch["rays_d"], batch["rgb"], idx % 5, 2.0, 6.0, 64, 128))
+        torch.manual_seed(400 + step)
+        lb = float(trb.step(batch["rays_o"], batch["rays_d"], batch["rgb"], idx % 5, 2.0, 6.0, 64, 128))
+        assert abs(la - lb) / lb <= 2e-4, (la, lb)
+        if step == 0:
+            ga, gb = ta.grad.double(), tb.grad.double()
+            rel = float((ga - gb).abs().max() / gb.abs().max())
+            cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
+            record("per_ray_embedding_table_grad", rel=rel, cos=cos)
+            assert rel <= 3e-2 and cos >= 0.999, (rel, cos)
+            assert float(gb.abs().sum(1).min()) > 0     # every one of the 5 rows received gradient
