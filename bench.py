@@ -513,14 +513,18 @@ def run_ours(args):
                 roof[label]["note"] = ("bf16x3 (fp32-parity split) issues 3 bf16 MMAs per trunk product, so the algorithmic frac is "
                                        "bounded by ~0.35; issued_frac is the tensor-pipe rate against the same peak")
         raw = ops.mlp_fwd(ws, packed, o_dev, dn, z_all, emb2, nerfw.models.resolve_mode(fine_mode))
-        # HBM-bound kernels on the same frame
-        cms = timed(lambda: ops.composite_fwd(raw, z_all), 5)
+        # HBM-bound kernels on the same frame, each timed ALONE like the copy kernel behind MEASURED_PEAKS.json's hbm_gbs
+        # (its "burst" figure): after seconds of power-capped tensor work the SM clock needs a moment to come back, and the
+        # resampling kernel is instruction-bound, so it is given the same idle start the peak measurement had
+        torch.cuda.synchronize()
+        time.sleep(0.5)
+        cms = timed(lambda: ops.composite_fwd(raw, z_all), 10)
         cbytes = z_all.numel() * 24.0 + n_rays * 20.0
-        rms = timed(lambda: ops.sample_pdf(z_coarse, w_coarse, N_IMPORTANCE, ur), 5)
+        rms = timed(lambda: ops.sample_pdf(z_coarse, w_coarse, N_IMPORTANCE, ur), 20)
         rbytes = n_rays * (3 * N_COARSE + 2 * N_IMPORTANCE) * 4.0
         g_rgb = torch.rand((n_rays, 3), device=dev)
         g_depth = torch.rand((n_rays, 1), device=dev)
-        bms = timed(lambda: ops.composite_bwd(raw, z_all, g_rgb, g_depth, None, None), 5)
+        bms = timed(lambda: ops.composite_bwd(raw, z_all, g_rgb, g_depth, None, None), 10)
         bbytes = z_all.numel() * 40.0
 
         def hb(nbytes, ms, **extra):
@@ -674,12 +678,18 @@ def run_ours(args):
                                                        appearance_embedding=emb_d, perturb=False, mlp_dtype=mode, u_rand=ud)
             _, depth_d32, _ = nerfw.volume_render(m_dense, od.to(dev), dd.to(dev), NEAR, FAR, N_COARSE, N_IMPORTANCE,
                                                   appearance_embedding=emb_d, perturb=False, mlp_dtype="fp32", u_rand=ud)
+            _, depth_dx3, _ = nerfw.volume_render(m_dense, od.to(dev), dd.to(dev), NEAR, FAR, N_COARSE, N_IMPORTANCE,
+                                                  appearance_embedding=emb_d, perturb=False, mlp_dtype="bf16x3", u_rand=ud)
         parity["dense"] = {"rays": n_d, "mean_acc": float(acc_od.mean()), "rgb": parity_stats(rgb_d, rgb_od),
                            "depth": parity_stats(depth_d, depth_od), "acc": parity_stats(ex_d["acc"], acc_od),
                            "depth_fp32_kernel": parity_stats(depth_d32, depth_od),
-                           "note": "rays over the bar are resampling discontinuities of the reference algorithm itself (the denom < 1e-5 "
-                                   "branch of src/ray_utils.py:136-137 and searchsorted ties flip on last-bit differences of the coarse "
-                                   "weights): the all-fp32 CUDA-core kernel (depth_fp32_kernel) shows the same tail"}
+                           "depth_bf16x3": parity_stats(depth_dx3, depth_od),
+                           "note": "depth_fp32_kernel / depth_bf16x3: the same rays through the all-fp32 CUDA-core kernel and the bf16x3 mode. "
+                                   "Their rays over the bar are resampling discontinuities of the reference algorithm itself (the "
+                                   "denom < 1e-5 branch of src/ray_utils.py:136-137 and searchsorted ties flip on last-bit differences of "
+                                   "the coarse weights).  The fp16 fine pass of `mixed` adds rays whose depth is ill-conditioned in sigma "
+                                   "(semi-transparent first surface in front of a second one: an fp16-level 1e-3 relative change of a "
+                                   "small sigma moves weight across a depth gap of ~1); DESIGN.md section 2"}
 
     value = world * n_rays * args.steps / (ms_total * 1e-3) / 1e6
     e2e_val = world * n_rays * args.steps / (e2e_ms * 1e-3) / 1e6

@@ -192,7 +192,7 @@ def test_checkpoint_resume_keeps_training(state_dict, oracle, tmp_path):
     for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert maxabs(pa, pb) <= 2e-6, k              # atomics order in the backward only
     assert maxabs(ta, tb) <= 2e-6
-    with pytest.raises(RuntimeError, match="shape"):
+    with pytest.raises(RuntimeError, match="expected"):
         load_checkpoint(path, mb, torch.nn.Parameter(torch.zeros(4, 32, device="cuda")))
 
 
