@@ -685,11 +685,12 @@ def run_ours(args):
                            "depth_fp32_kernel": parity_stats(depth_d32, depth_od),
                            "depth_bf16x3": parity_stats(depth_dx3, depth_od),
                            "note": "depth_fp32_kernel / depth_bf16x3: the same rays through the all-fp32 CUDA-core kernel and the bf16x3 mode. "
-                                   "Their rays over the bar are resampling discontinuities of the reference algorithm itself (the "
-                                   "denom < 1e-5 branch of src/ray_utils.py:136-137 and searchsorted ties flip on last-bit differences of "
-                                   "the coarse weights).  The fp16 fine pass of `mixed` adds rays whose depth is ill-conditioned in sigma "
-                                   "(semi-transparent first surface in front of a second one: an fp16-level 1e-3 relative change of a "
-                                   "small sigma moves weight across a depth gap of ~1); DESIGN.md section 2"}
+                                   "Rays over the bar are resampling discontinuities of the reference algorithm itself: in an opaque "
+                                   "scene most bins carry only the +1e-5 floor, so `denom < 1e-5` (src/ray_utils.py:136-137) sits exactly "
+                                   "on its threshold and flips with the last bit of the cdf, moving that fine sample by up to one bin; "
+                                   "the more an implementation's coarse weights differ from the CPU's in the last bits (fp32 kernel "
+                                   "1e-7, bf16x3 1e-6 relative), the more such flips.  bf16x3 and mixed show the same tail, i.e. the "
+                                   "fp16 fine pass adds nothing to it; DESIGN.md section 2"}
 
     value = world * n_rays * args.steps / (ms_total * 1e-3) / 1e6
     e2e_val = world * n_rays * args.steps / (e2e_ms * 1e-3) / 1e6
