@@ -520,8 +520,10 @@ def run_ours(args):
         time.sleep(0.5)
         cms = timed(lambda: ops.composite_fwd(raw, z_all), 10)
         cbytes = z_all.numel() * 24.0 + n_rays * 20.0
-        rms = timed(lambda: ops.sample_pdf(z_coarse, w_coarse, N_IMPORTANCE, ur), 20)
-        rbytes = n_rays * (3 * N_COARSE + 2 * N_IMPORTANCE) * 4.0
+        # the launch the step performs: with coarse re-use it also returns the NI new depths on their own (z_fine), which the
+        # fine-pass MLP launch reads: read w, z (N each) and u (NI), write the merged row (N + NI) [+ z_fine (NI)]
+        rms = timed(lambda: ops.sample_pdf(z_coarse, w_coarse, N_IMPORTANCE, ur, want_zfine=reused), 20)
+        rbytes = n_rays * (3 * N_COARSE + (3 if reused else 2) * N_IMPORTANCE) * 4.0
         g_rgb = torch.rand((n_rays, 3), device=dev)
         g_depth = torch.rand((n_rays, 1), device=dev)
         bms = timed(lambda: ops.composite_bwd(raw, z_all, g_rgb, g_depth, None, None), 10)
@@ -530,7 +532,8 @@ def run_ours(args):
         def hb(nbytes, ms, **extra):
             return {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": ms, **extra}
-        hbm = {"composite_fwd": hb(cbytes, cms), "composite_bwd": hb(bbytes, bms), "sample_pdf": hb(rbytes, rms)}
+        hbm = {"composite_fwd": hb(cbytes, cms), "composite_bwd": hb(bbytes, bms),
+               "sample_pdf": hb(rbytes, rms, bytes_per_ray=rbytes / n_rays, outputs="merged row + z_fine" if reused else "merged row")}
         if reused:
             raw_c = ops.mlp_fwd(ws, packed, o_dev, dn, z_coarse, emb2, nerfw.models.resolve_mode(coarse_mode))
             raw_f = ops.mlp_fwd(ws, packed, o_dev, dn, z_new, emb2, nerfw.models.resolve_mode(fine_mode))
