@@ -136,7 +136,9 @@ def render_path_to_dir(model, dataset, config, output_dir, num_frames=120, quali
     figure: camera paths circle / spiral / horizontal_only / hemisphere, quality presets (preview: half the coarse samples,
     no fine pass, no jitter; medium / high: jittered, run.py:90-105), focal scaled to the requested width (run.py:198-199),
     files `rgb_%03d.png`, `raw/rgb_%03d.png` (raw_output) and `raw/depth_%03d.npy` (save_depth, fp32 -- what a
-    depth-aware post-process should read instead of an 8-bit PNG)."""
+    depth-aware post-process should read instead of an 8-bit PNG).  As in the reference, every one of the `num_frames`
+    poses is rendered and frame i is NAMED start_frame + i; `end_frame` only appears in the reference's progress messages
+    (run.py:161-166) and is accepted for signature compatibility."""
     os.makedirs(output_dir, exist_ok=True)
     coarse = model[0] if isinstance(model, (tuple, list)) else model
     dev = coarse.rgb_linear.weight.device
@@ -144,14 +146,13 @@ def render_path_to_dir(model, dataset, config, output_dir, num_frames=120, quali
     n_samples = config.num_samples // 2 if quality == "preview" else config.num_samples
     n_importance = 0 if quality == "preview" else config.num_importance
     perturb = quality != "preview"
-    end_frame = num_frames if end_frame is None else end_frame
     poses = path_poses(camera_path, num_frames, getattr(config, "scene", ""), spiral_loops, height_range)
     focal = focal0 * (width / w0)
     rank, world = world_info(group)
     with FrameWriter(output_dir) as wr:
         for i in range(len(poses)):
             idx = start_frame + i
-            if idx >= end_frame or i % world != rank:
+            if i % world != rank:
                 continue
             rgb, depth, _ = render_frame(model, height, width, focal, poses[i], near, far, n_samples, n_importance,
                                          appearance_embedding=emb, mlp_dtype=mlp_dtype, perturb=perturb, generator=generator)

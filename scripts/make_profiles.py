@@ -52,9 +52,11 @@ if os.path.exists(raw):
           f"# Round {int(TAG[1:])} — ncu --set full, sample_pdf_kernel at 640 000 rays, 64 + 128\n\n"
           f"Command: {CMD.format('time_pdf.py')}.\n\n" + run("ncu_summary.py", raw))
 
-# launch list of bench.py itself
-lst = os.path.join(OUT, "launches_bench.csv")
-if os.path.exists(lst):
+# launch lists (whole bench command; one step = one whole frame)
+def launch_table(csv_name, out_name, title, blurb):
+    lst = os.path.join(OUT, csv_name)
+    if not os.path.exists(lst):
+        return
     rows = [r for r in csv.reader(open(lst)) if len(r) > 10]
     hdr = rows[0]
     ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
@@ -72,10 +74,19 @@ if os.path.exists(lst):
         agg[name][1] += t_ms
     total = sum(v[1] for v in agg.values())
     n = sum(v[0] for v in agg.values())
-    text = (f"# Round {int(TAG[1:])} — ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (whole command)\n\n"
+    text = (f"# Round {int(TAG[1:])} -- {title}\n\n"
             f"`ncu --metrics gpu__time_duration.sum --clock-control none`, {n} launches, {total:.1f} ms of device time (cold-cache, serialised: compare shares).\n"
-            "The command contains the timed frames, the e2e frames, the per-kernel roofline loops, the bf16 frames, the 157-chunk frame and the training steps.\n\n"
-            "| kernel | launches | total ms | share |\n|---|---|---|---|\n")
+            f"{blurb}\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
     for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         text += f"| `{name}` | {c} | {t:.3f} | {100 * t / total:.2f} % |\n"
-    write(f"{TAG}_launches_bench.md", text)
+    write(out_name, text)
+
+
+launch_table("launches_bench.csv", f"{TAG}_launches_bench.md",
+             "ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --quick` (whole command)",
+             "The command contains the timed frames, the e2e frames, the per-kernel roofline loops, the other-mode frames, the 157-chunk frame, "
+             "the 256+512 stress call and the training steps.")
+launch_table("launches_step.csv", f"{TAG}_launches_step.md",
+             "ncu launch list of ONE step: one whole 800x800 frame, 64+128, default mode (`python scripts/profile_frame.py --mode mixed --rows 800`)",
+             "Default path: coarse pass `mlp_tc_fwd_kernel<1,0,0>` (bf16x3, 64 depths, full outputs), resampling, fine pass `mlp_tc_fwd_kernel<0,1,0>` "
+             "(fp16, the 128 new depths), merge, compositing.  bench.py's `roofline.share_of_step` is the live counterpart of the share column.")

@@ -258,3 +258,32 @@ def test_train_nerf_steps_match_reference(golden, monkeypatch, mode):
     assert emb_err <= 3 * 2 * cfg.learning_rate and maxabs(sd["rgb_linear.bias"], g["rgb_bias"]) <= 3 * 2 * cfg.learning_rate
     assert norm_rel <= 1e-3
     assert torch.equal(ds.appearance_embeddings.detach()[0], torch.from_numpy(g["emb_table0"][0]))  # untouched rows stay
+
+
+@pytest.mark.gpu
+def test_render_path_driver_files_and_quality_presets(golden, tmp_path):
+    """nerfw.frame.render_path_to_dir: run.py::render_path's camera paths, quality presets and file names (run.py:233-269:
+    `rgb_%03d.png`, `raw/rgb_%03d.png`, `raw/depth_%03d.npy`), written off the render thread; frame range selection."""
+    from PIL import Image
+    from nerfw.frame import render_frame, render_path_to_dir
+    from nerfw.camera import path_poses
+    g = golden("callers_spiral")
+    model, cfg = _seed0_model()
+    cfg.scene, cfg.num_samples, cfg.num_importance = "hotdog", 32, 16
+    ds = _Dataset(24, 24, g["emb_table"])
+    out = str(tmp_path / "frames")
+    files = render_path_to_dir(model, ds, cfg, out, num_frames=4, quality="preview", width=16, height=12, start_frame=2,
+                               save_depth=True, raw_output=True, camera_path="hemisphere")
+    rel = sorted(os.path.relpath(f, out) for f in files)
+    want = sorted([f"rgb_{i:03d}.png" for i in range(2, 6)] + [os.path.join("raw", f"rgb_{i:03d}.png") for i in range(2, 6)] +
+                  [os.path.join("raw", f"depth_{i:03d}.npy") for i in range(2, 6)])
+    assert rel == want
+    img = np.asarray(Image.open(os.path.join(out, "rgb_003.png")))
+    depth = np.load(os.path.join(out, "raw", "depth_003.npy"))
+    assert img.shape == (12, 16, 3) and img.dtype == np.uint8 and depth.shape == (12, 16) and depth.dtype == np.float32
+    # frame index 3 = pose 1 of the path (start_frame offsets the NAMES, run.py:166); preview = half the samples, no fine pass
+    poses = path_poses("hemisphere", 4, "hotdog")
+    rgb, dep, _ = render_frame(model, 12, 16, ds.focal * (16 / ds.W), poses[1], ds.near, ds.far, 16, 0,
+                               appearance_embedding=ds.appearance_embeddings[0].detach().cuda())
+    assert np.array_equal(img, (rgb.cpu() * 255).numpy().astype(np.uint8)) and np.array_equal(depth, dep.cpu().numpy())
+    assert np.array_equal(np.asarray(Image.open(os.path.join(out, "raw", "rgb_003.png"))), img)
