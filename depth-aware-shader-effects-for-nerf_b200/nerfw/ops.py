@@ -22,6 +22,26 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(device: torch.device):
+    """Device guard for a launch: a no-op when `device` is already current (the common case -- entering
+    torch.cuda.device() costs several microseconds per launch, which is what a 4096-ray chunk loop is made of)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -61,7 +81,7 @@ def raygen(height: int, width: int, focal: float, c2w: torch.Tensor, device: tor
     if c.shape[-2:] not in ((4, 4), (3, 4)):
         raise ValueError(f"c2w must be (4,4) or (3,4), got {tuple(c2w.shape)}")
     host = (C.c_float * 12)(*c[:3, :4].reshape(-1).tolist())
-    with torch.cuda.device(device):
+    with _on(device):
         dirs = torch.empty((height, width, 3), dtype=torch.float32, device=device)
         origins = torch.empty((height, width, 3), dtype=torch.float32, device=device) if want_origins else None
         # `focal` arrives as a python/numpy double; the reference's tensor/scalar division rounds it to fp32 first
@@ -73,14 +93,14 @@ def raygen(height: int, width: int, focal: float, c2w: torch.Tensor, device: tor
 def normalize_dirs(d: torch.Tensor) -> torch.Tensor:
     d = _f32c(d, "rays_d")
     out = torch.empty_like(d)
-    with torch.cuda.device(d.device):
+    with _on(d.device):
         check(lib().nerfw_normalize_dirs(d.data_ptr(), d.numel() // 3, out.data_ptr(), _stream()))
     return out
 
 
 def depth_table(near: float, far: float, n: int, device: torch.device) -> torch.Tensor:
     """near + linspace(0,1,N)*(far-near) computed with HOST torch (bit-identical to src/ray_utils.py:69-70), cached."""
-    key = (float(near), float(far), int(n), str(device))
+    key = (float(near), float(far), int(n), device.index)
     tab = _ZTAB_CACHE.get(key)
     if tab is None:
         t = torch.linspace(0.0, 1.0, int(n))
@@ -91,7 +111,7 @@ def depth_table(near: float, far: float, n: int, device: torch.device) -> torch.
 
 def u_table(n_importance: int, device: torch.device) -> torch.Tensor:
     """linspace(0,1,NI+1)[:-1] from host torch (src/ray_utils.py:115), cached."""
-    key = (int(n_importance), str(device))
+    key = (int(n_importance), device.index)
     tab = _ULIN_CACHE.get(key)
     if tab is None:
         tab = torch.linspace(0.0, 1.0, int(n_importance) + 1)[:-1].contiguous().to(device)
@@ -109,7 +129,7 @@ def stratified(rays_o: Optional[torch.Tensor], rays_d: Optional[torch.Tensor], z
         t_rand = _f32c(t_rand, "t_rand")
         if tuple(t_rand.shape) != (n_rays, n):
             raise ValueError(f"t_rand must be ({n_rays},{n}), got {tuple(t_rand.shape)}")
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib().nerfw_stratified(_ptr(rays_o), _ptr(rays_d), ztab.data_ptr(), _ptr(t_rand), n_rays, n,
                                      z.data_ptr(), _ptr(pts), _stream()))
     return z, pts
@@ -118,7 +138,7 @@ def stratified(rays_o: Optional[torch.Tensor], rays_d: Optional[torch.Tensor], z
 def ray_points(rays_o: torch.Tensor, rays_d: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
     b, n = z.shape
     pts = torch.empty((b, n, 3), dtype=torch.float32, device=z.device)
-    with torch.cuda.device(z.device):
+    with _on(z.device):
         check(lib().nerfw_ray_points(rays_o.data_ptr(), rays_d.data_ptr(), z.data_ptr(), b, n, pts.data_ptr(), _stream()))
     return pts
 
@@ -144,7 +164,7 @@ def sample_pdf(z_vals: torch.Tensor, weights: torch.Tensor, n_importance: int, u
         zf = torch.empty((b, n_importance), dtype=torch.float32, device=dev)
     ulin = u_table(n_importance, dev)
     fn = lib().nerfw_sample_pdf_general if general_path else lib().nerfw_sample_pdf
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(fn(z_vals.data_ptr(), weights.data_ptr(), ulin.data_ptr(), u_rand.data_ptr(), b, n,
                  int(n_importance), out.data_ptr(), _ptr(inds), _ptr(zf), _ptr(cdf), _stream()))
     if want_aux:
@@ -159,7 +179,7 @@ def merge_raw(z_coarse: torch.Tensor, raw_coarse: torch.Tensor, z_fine: torch.Te
     b, n = z_coarse.shape
     ni = z_fine.shape[1]
     out = torch.empty((b * (n + ni), 4), dtype=torch.float32, device=z_coarse.device)
-    with torch.cuda.device(z_coarse.device):
+    with _on(z_coarse.device):
         check(lib().nerfw_merge_raw(_f32c(z_coarse, "z_coarse").data_ptr(), _f32c(raw_coarse, "raw_coarse").data_ptr(),
                                     _f32c(z_fine, "z_fine").data_ptr(), _f32c(raw_fine, "raw_fine").data_ptr(), b, n, ni,
                                     out.data_ptr(), _stream()))
@@ -175,7 +195,7 @@ def unmerge_raw(z_coarse: torch.Tensor, z_fine: torch.Tensor, d_merged: torch.Te
     if d_coarse is None:
         d_coarse = torch.empty((b * n, 4), dtype=torch.float32, device=z_coarse.device)
     d_fine = torch.empty((b * ni, 4), dtype=torch.float32, device=z_coarse.device)
-    with torch.cuda.device(z_coarse.device):
+    with _on(z_coarse.device):
         check(lib().nerfw_unmerge_raw(z_coarse.data_ptr(), z_fine.data_ptr(), _f32c(d_merged, "d_merged").data_ptr(), b, n, ni,
                                       int(acc), d_coarse.data_ptr(), d_fine.data_ptr(), _stream()))
     return d_coarse, d_fine
@@ -188,7 +208,7 @@ def posenc(x: torch.Tensor, levels: int, include_input: bool = True) -> torch.Te
     flat = x.reshape(-1, dim)
     width = dim * ((1 if include_input else 0) + 2 * levels)
     out = torch.empty((flat.shape[0], width), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib().nerfw_posenc(flat.data_ptr(), flat.shape[0], dim, int(levels), int(bool(include_input)),
                                  out.data_ptr(), _stream()))
     return out.reshape(*lead, width)
@@ -271,7 +291,7 @@ def pack_weights(params, out: Optional[torch.Tensor] = None, device=None) -> tor
     if out is None:
         out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     ws = weights_struct(params)
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib().nerfw_pack_weights(C.byref(ws), out.data_ptr(), out.numel(), _stream()))
     return out
 
@@ -295,7 +315,7 @@ def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: to
     masks = None
     if want_masks:
         masks = torch.empty(int(lib().nerfw_mlp_mask_bytes(n_rays, n_samples)), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib().nerfw_mlp_fwd(C.byref(ws), _ptr(packed), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows,
                                   n_rays, n_samples, int(mode) | (0x100 if sigma_only and int(mode) != 0 else 0), raw.data_ptr(), _ptr(masks), ws_buf.data_ptr(), wbytes,
                                   _stream()))
@@ -315,7 +335,7 @@ def mlp_bwd(params: dict, grads: dict, p: torch.Tensor, d: torch.Tensor, z: Opti
     ws_buf = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     ws = weights_struct(params)
     gs = weights_struct(grads)
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib().nerfw_mlp_bwd(C.byref(ws), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows, n_rays, n_samples,
                                   d_raw.data_ptr(), C.byref(gs), _ptr(d_emb), ws_buf.data_ptr(), wbytes, _stream()))
 
@@ -333,7 +353,7 @@ def mlp_bwd_tc(params: dict, grads: dict, packed: torch.Tensor, p: torch.Tensor,
     ws_buf = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     ws = weights_struct(params)
     gs = weights_struct(grads)
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib().nerfw_mlp_bwd_tc(C.byref(ws), packed.data_ptr(), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows,
                                      n_rays, n_samples, d_raw.data_ptr(), _ptr(masks), C.byref(gs), _ptr(d_emb),
                                      ws_buf.data_ptr(), wbytes, _stream()))
@@ -347,7 +367,7 @@ def composite_fwd(raw: torch.Tensor, z: torch.Tensor, want_weights: bool = True)
     depth = torch.empty((b, 1), dtype=torch.float32, device=dev)
     acc = torch.empty((b, 1), dtype=torch.float32, device=dev)
     w = torch.empty((b, n), dtype=torch.float32, device=dev) if want_weights else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib().nerfw_composite_fwd(raw.data_ptr(), z.data_ptr(), b, n, rgb.data_ptr(), depth.data_ptr(),
                                         acc.data_ptr(), _ptr(w), _stream()))
     return rgb, depth, acc, w
@@ -357,7 +377,7 @@ def composite_bwd(raw: torch.Tensor, z: torch.Tensor, d_rgb: torch.Tensor, d_dep
                   d_acc: Optional[torch.Tensor], d_w: Optional[torch.Tensor]) -> torch.Tensor:
     b, n = z.shape
     d_raw = torch.empty((b * n, 4), dtype=torch.float32, device=z.device)
-    with torch.cuda.device(z.device):
+    with _on(z.device):
         check(lib().nerfw_composite_bwd(raw.data_ptr(), z.data_ptr(), b, n, d_rgb.data_ptr(), _ptr(d_depth), _ptr(d_acc),
                                         _ptr(d_w), d_raw.data_ptr(), _stream()))
     return d_raw
@@ -366,7 +386,7 @@ def composite_bwd(raw: torch.Tensor, z: torch.Tensor, d_rgb: torch.Tensor, d_dep
 # ------------------------------------------------------------------------------------------------ training helpers
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
               lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0) -> None:
-    with torch.cuda.device(param.device):
+    with _on(param.device):
         check(lib().nerfw_adam(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                param.numel(), lr, betas[0], betas[1], eps, int(step), grad_scale, _stream()))
 
@@ -376,7 +396,7 @@ def mse(rgb: torch.Tensor, target: torch.Tensor, loss_scale: float = 1.0, want_g
     target = _f32c(target, "target")
     loss = torch.empty(1, dtype=torch.float32, device=rgb.device)
     d = torch.empty_like(rgb) if want_grad else None
-    with torch.cuda.device(rgb.device):
+    with _on(rgb.device):
         check(lib().nerfw_mse(rgb.data_ptr(), target.data_ptr(), rgb.numel(), loss_scale, loss.data_ptr(), _ptr(d), _stream()))
     return loss, d
 
@@ -384,7 +404,7 @@ def mse(rgb: torch.Tensor, target: torch.Tensor, loss_scale: float = 1.0, want_g
 def quantize_u8(x: torch.Tensor) -> torch.Tensor:
     x = _f32c(x, "x")
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib().nerfw_quantize_u8(x.data_ptr(), x.numel(), out.data_ptr(), _stream()))
     return out
 
@@ -395,7 +415,7 @@ def selftest_umma_mn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
     at = at.contiguous()
     bt = bt.contiguous()
     d = torch.empty((128, bt.shape[1]), dtype=torch.float32, device=at.device)
-    with torch.cuda.device(at.device):
+    with _on(at.device):
         check(lib().nerfw_selftest_umma_mn(at.data_ptr(), bt.data_ptr(), bt.shape[1], at.shape[0], d.data_ptr(), _stream()))
     return d
 
@@ -406,7 +426,7 @@ def selftest_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     a = a.contiguous()
     b = b.contiguous()
     d = torch.empty((128, b.shape[0]), dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
+    with _on(a.device):
         check(lib().nerfw_selftest_umma(a.data_ptr(), b.data_ptr(), b.shape[0], a.shape[1], int(mode), d.data_ptr(), _stream()))
     return d
 
@@ -422,7 +442,7 @@ def max_f32(x: torch.Tensor) -> torch.Tensor:
     """Device scalar max(x) (depth.max() of src/post_processor.py:64,408,476); no host sync."""
     x = _f32c(x, "x")
     out = torch.empty(1, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib().nerfw_max_f32(x.data_ptr(), x.numel(), out.data_ptr(), _stream()))
     return out
 
@@ -436,7 +456,7 @@ def fog(image: torch.Tensor, depth: torch.Tensor, depth_max: torch.Tensor, fog_s
         raise ValueError(f"image must hold 3 values per depth pixel, got {tuple(image.shape)} vs {tuple(depth.shape)}")
     out = torch.empty_like(image)
     color = (C.c_float * 3)(*[float(c) for c in fog_color])
-    with torch.cuda.device(depth.device):
+    with _on(depth.device):
         check(lib().nerfw_fog(image.data_ptr(), depth.data_ptr(), depth_max.data_ptr(), n, float(fog_start), float(power),
                               float(visibility), color, out.data_ptr(), _stream()))
     return out
@@ -452,7 +472,7 @@ def depth_edges(depth: torch.Tensor, depth_max: torch.Tensor, bilateral_d: int =
     mag = torch.empty_like(depth)
     mag_max = torch.empty(1, dtype=torch.float32, device=depth.device)
     filtered = torch.empty_like(depth) if bilateral_d else None
-    with torch.cuda.device(depth.device):
+    with _on(depth.device):
         check(lib().nerfw_depth_edges(depth.data_ptr(), depth_max.data_ptr(), h, w, int(bilateral_d), float(sigma_color),
                                       float(sigma_space), _ptr(filtered), mag.data_ptr(), mag_max.data_ptr(), _stream()))
     return mag, mag_max, filtered
@@ -464,7 +484,7 @@ def toon(image: torch.Tensor, mag: torch.Tensor, mag_max: torch.Tensor, levels: 
     if tuple(image.shape) != (h, w, 3):
         raise ValueError(f"image must be ({h},{w},3), got {tuple(image.shape)}")
     out = torch.empty_like(image)
-    with torch.cuda.device(image.device):
+    with _on(image.device):
         check(lib().nerfw_toon(image.data_ptr(), mag.data_ptr(), mag_max.data_ptr(), h, w, int(levels), float(edge_strength),
                                out.data_ptr(), _stream()))
     return out
@@ -483,7 +503,7 @@ def hologram(image: torch.Tensor, mag, mag_max, row_scale: torch.Tensor, col_hit
         if tuple(noise.shape) != (h, w, 3):
             raise ValueError(f"noise must be ({h},{w},3)")
     out = torch.empty_like(image)
-    with torch.cuda.device(image.device):
+    with _on(image.device):
         check(lib().nerfw_hologram(image.data_ptr(), _ptr(mag), _ptr(mag_max), row_scale.data_ptr(), _ptr(col_hits),
                                    _ptr(noise), h, w, out.data_ptr(), _stream()))
     return out
