@@ -18,7 +18,15 @@ _ZTAB_CACHE: dict = {}
 _ULIN_CACHE: dict = {}
 
 
+# Raw handles without torch's Python-level wrappers: torch.cuda.current_stream() builds a Stream object through several
+# layers of device-index normalisation (~5 us), and every launch needs the handle.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream() -> int:
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -37,7 +45,7 @@ def _on(device: torch.device):
     """Device guard for a launch: a no-op when `device` is already current (the common case -- entering
     torch.cuda.device() costs several microseconds per launch, which is what a 4096-ray chunk loop is made of)."""
     idx = device.index
-    if idx is None or idx == torch.cuda.current_device():
+    if idx is None or idx == (_raw_device() if _raw_device is not None else torch.cuda.current_device()):
         return _NO_GUARD
     return torch.cuda.device(device)
 

@@ -17,12 +17,19 @@ def call():
         return nerfw.volume_render(m, o, d, 2.0, 6.0, 64, 128, appearance_embedding=emb, perturb=False)
 for _ in range(20): call()
 torch.cuda.synchronize()
-t0 = time.perf_counter()
-for _ in range(300): call()
-dt = (time.perf_counter() - t0) / 300 * 1e6
+best = 1e9
+for _ in range(10):          # bursts of 20 calls: the launch queue never fills, so this is host time only
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20): call()
+    best = min(best, (time.perf_counter() - t0) / 20 * 1e6)
 torch.cuda.synchronize()
-print(f"enqueue time per call: {dt:.1f} us")
-pr = cProfile.Profile(); pr.enable()
-for _ in range(300): call()
-pr.disable(); torch.cuda.synchronize()
+print(f"enqueue time per call: {best:.1f} us")
+pr = cProfile.Profile()
+for _ in range(15):
+    torch.cuda.synchronize()
+    pr.enable()
+    for _ in range(20): call()
+    pr.disable()
+torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("tottime").print_stats(22)
