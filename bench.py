@@ -534,6 +534,9 @@ def run_ours(args):
                     "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": ms, **extra}
         hbm = {"composite_fwd": hb(cbytes, cms), "composite_bwd": hb(bbytes, bms),
                "sample_pdf": hb(rbytes, rms, bytes_per_ray=rbytes / n_rays, outputs="merged row + z_fine" if reused else "merged row")}
+        if reused:   # the plain form of the same kernel (merged row only, 1 792 B/ray: SURVEY.md 8d's figure), for comparison
+            pms = timed(lambda: ops.sample_pdf(z_coarse, w_coarse, N_IMPORTANCE, ur), 20)
+            hbm["sample_pdf_merged_row_only"] = hb(n_rays * (3 * N_COARSE + 2 * N_IMPORTANCE) * 4.0, pms, bytes_per_ray=1792.0)
         if reused:
             raw_c = ops.mlp_fwd(ws, packed, o_dev, dn, z_coarse, emb2, nerfw.models.resolve_mode(coarse_mode))
             raw_f = ops.mlp_fwd(ws, packed, o_dev, dn, z_new, emb2, nerfw.models.resolve_mode(fine_mode))
@@ -704,6 +707,15 @@ def run_ours(args):
     e2e_val = world * n_rays * args.steps / (e2e_ms * 1e-3) / 1e6
     dominant = max(("fine", "coarse"), key=lambda k: roof[k]["kernel_ms"])
     roof[dominant]["share_of_step"] = roof[dominant]["kernel_ms"] / (ms_total / args.steps)
+    # both MLP launches of the step together (the same kernel template in two arithmetic instantiations)
+    mlp_ms = roof["fine"]["kernel_ms"] + roof["coarse"]["kernel_ms"]
+    mlp_flops = FLOP_PER_SAMPLE * float(roof["fine"]["samples_per_launch"] + roof["coarse"]["samples_per_launch"])
+    roof[dominant]["step_mlp_launches"] = {
+        "kernel_ms": mlp_ms, "share_of_step": mlp_ms / (ms_total / args.steps), "achieved": mlp_flops / (mlp_ms * 1e-3) / 1e12,
+        "frac": mlp_flops / (mlp_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+        "issued_frac": (roof["fine"]["issued"] * roof["fine"]["kernel_ms"] + roof["coarse"]["issued"] * roof["coarse"]["kernel_ms"]) / mlp_ms
+                       / peaks["bf16_tflops_sustained"],
+        "note": "coarse launch: bf16x3 (3 MMAs per product for fp32 parity, at the sustained tensor rate); fine launch: one fp16 MMA per product"}
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
