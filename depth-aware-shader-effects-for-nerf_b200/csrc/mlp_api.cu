@@ -52,8 +52,10 @@ extern "C" int nerfw_mlp_fwd(const NerfwWeights* w, const void* packed, const fl
       set_error("nerfw_mlp_fwd: workspace of %zu bytes, need %zu", workspace_bytes, nerfw_mlp_workspace_bytes(n_rays, emb_rows));
       return NERFW_ESIZE;
     }
-    rc = launch_app_offset(*w, emb, emb_rows, reinterpret_cast<float*>(workspace), as_stream(stream));
-    if (rc) return rc;
+    if (!(mode & NERFW_MLP_APP_CACHED)) {   // else: the offsets of these rows are already in the workspace
+      rc = launch_app_offset(*w, emb, emb_rows, reinterpret_cast<float*>(workspace), as_stream(stream));
+      if (rc) return rc;
+    }
     app_off = reinterpret_cast<const float*>(workspace);
   }
   const int mode_flags = mode;

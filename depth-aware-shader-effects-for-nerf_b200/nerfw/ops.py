@@ -305,10 +305,14 @@ def pack_weights(params, out: Optional[torch.Tensor] = None, device=None) -> tor
 
 
 def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: torch.Tensor, z: Optional[torch.Tensor],
-            emb: Optional[torch.Tensor], mode: int, want_masks: bool = False, sigma_only: bool = False):
+            emb: Optional[torch.Tensor], mode: int, want_masks: bool = False, sigma_only: bool = False,
+            app_ws: Optional[list] = None):
     """raw (S,4) = (r,g,b,sigma).  p,d: (B,3) rays with z (B,N), or (S,3) samples with z None.
     want_masks (tensor-core modes): also return the ReLU gate words for nerfw_mlp_bwd_tc -> (raw, masks).
-    sigma_only (tensor-core modes, inference): NERFW_MLP_SIGMA_ONLY -- raw = (0, 0, 0, sigma), direction layer skipped."""
+    sigma_only (tensor-core modes, inference): NERFW_MLP_SIGMA_ONLY -- raw = (0, 0, 0, sigma), direction layer skipped.
+    app_ws: a one-element list the caller keeps for launches that share weights AND embedding rows (the coarse and fine
+    launch of one render; the chunks of one frame): the first launch stores its workspace (holding the per-row rgb-logit
+    offsets) in it, later ones pass NERFW_MLP_APP_CACHED and skip the offset kernel."""
     dev = p.device
     n_rays = p.shape[0]
     n_samples = z.shape[1] if z is not None else 1
@@ -317,16 +321,25 @@ def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: to
     emb_rows = 0
     if emb is not None:
         emb_rows = emb.shape[0]
+    flags = int(mode) | (0x100 if sigma_only and int(mode) != 0 else 0)
     wbytes = _mlp_workspace_bytes(n_rays, emb_rows)
-    ws_buf = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    stream = _stream()
+    # re-use only on the stream that wrote the offsets (stream order is what makes them visible to this launch)
+    if app_ws is not None and emb is not None and app_ws[0] is not None and app_ws[0][1] == stream and app_ws[0][0].numel() >= wbytes:
+        ws_buf = app_ws[0][0]
+        flags |= 0x200
+    else:
+        ws_buf = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        if app_ws is not None:
+            app_ws[0] = (ws_buf, stream)
     ws = weights_struct(params)
     masks = None
     if want_masks:
         masks = torch.empty(int(lib().nerfw_mlp_mask_bytes(n_rays, n_samples)), dtype=torch.uint8, device=dev)
     with _on(dev):
         check(lib().nerfw_mlp_fwd(C.byref(ws), _ptr(packed), p.data_ptr(), d.data_ptr(), _ptr(z), _ptr(emb), emb_rows,
-                                  n_rays, n_samples, int(mode) | (0x100 if sigma_only and int(mode) != 0 else 0), raw.data_ptr(), _ptr(masks), ws_buf.data_ptr(), wbytes,
-                                  _stream()))
+                                  n_rays, n_samples, flags, raw.data_ptr(), _ptr(masks), ws_buf.data_ptr(), ws_buf.numel(),
+                                  stream))
     if want_masks:
         return raw, masks
     return raw

@@ -25,7 +25,8 @@ def _shade(model: NeRF, o, d, z, emb, mode, role="single", sigma_only=False):
     packed = model.packed_weights() if mode_id != 0 else None
     if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or (emb is not None and emb.requires_grad)):
         return RenderFn.apply(mode_id, names, o, d, z, emb, packed, *tensors)
-    raw = ops.mlp_fwd(ws, packed, o, d, z, None if emb is None else emb.detach(), mode_id, sigma_only=sigma_only)
+    raw = ops.mlp_fwd(ws, packed, o, d, z, None if emb is None else emb.detach(), mode_id, sigma_only=sigma_only,
+                      app_ws=model.app_workspace(emb, packed))
     return ops.composite_fwd(raw, z, want_weights=True)
 
 
@@ -43,10 +44,11 @@ def _render_reusing_coarse(model: NeRF, o, d, z, emb, mode, n_importance, u_rand
                                                                                    ur.float().contiguous(), *tensors)
     else:
         e = None if emb is None else emb.detach()
-        raw_c = ops.mlp_fwd(params, packed, o, d, z, e, mode_c)
+        app_ws = model.app_workspace(emb, packed)
+        raw_c = ops.mlp_fwd(params, packed, o, d, z, e, mode_c, app_ws=app_ws)
         rgb_c, depth_c, acc_c, w_c = ops.composite_fwd(raw_c, z, want_weights=True)
         z_all, z_new = ops.sample_pdf(z, w_c, n_importance, ur, want_zfine=True)       # src/ray_utils.py:90-149
-        raw_f = ops.mlp_fwd(params, packed, o, d, z_new, e, mode_f)
+        raw_f = ops.mlp_fwd(params, packed, o, d, z_new, e, mode_f, app_ws=app_ws)
         raw = ops.merge_raw(z, raw_c, z_new, raw_f)
         rgb, depth, acc, w = ops.composite_fwd(raw, z_all, want_weights=True)
     extras = {"rgb_coarse": rgb_c.reshape(*orig_shape[:-1], 3), "depth_coarse": depth_c.reshape(*orig_shape[:-1], 1),

@@ -46,6 +46,10 @@ enum {
 /* OR into `mode` (tensor-core modes, inference): skip the direction layer and the rgb head, raw = (0, 0, 0, sigma).  All the
  * coarse pass of a hierarchical render needs: its weights place the fine samples, its colour is never looked at. */
 #define NERFW_MLP_SIGMA_ONLY 0x100
+/* OR into `mode` of nerfw_mlp_fwd when `workspace` still holds the per-embedding-row rgb-logit offsets an earlier
+ * nerfw_mlp_fwd call wrote for the SAME embedding rows and the SAME weights (the coarse and the fine launch of one render,
+ * or consecutive 4096-ray chunks of one frame): the small offset kernel is not launched again. */
+#define NERFW_MLP_APP_CACHED 0x200
 
 /* Architecture constants the kernels are specialised for (config.py:10-33 defaults). */
 #define NERFW_HIDDEN 256

@@ -321,3 +321,33 @@ def test_fp16_mode_saturates_instead_of_overflowing(state_dict):
             m.mlp_mode = mode
             rgb, sigma = m(x, d, emb.cuda())
             assert bool(torch.isfinite(rgb).all()) and bool(torch.isfinite(sigma).all()), mode
+
+
+def test_appearance_offsets_are_cached_per_embedding_and_weights(cuda_model):
+    """The per-embedding rgb-logit offsets are computed once for launches that share weights and embedding rows
+    (NERFW_MLP_APP_CACHED): a second call launches one kernel fewer and returns the same bits; changing the embedding's
+    values (in place: version bump; or another tensor) or the weights recomputes them."""
+    from nerfw import ops
+    model, emb = cuda_model
+    x = torch.rand(500, 3, device="cuda") * 4 - 2
+    d = torch.nn.functional.normalize(torch.randn(500, 3, device="cuda"), dim=-1)
+    e = emb.clone()
+    with torch.no_grad():
+        model.invalidate_packed()
+        n0 = ops.launch_count()
+        a = model.run_mlp(x, d, None, e.unsqueeze(0), "bf16x3")
+        n1 = ops.launch_count()
+        b = model.run_mlp(x, d, None, e.unsqueeze(0), "bf16x3")
+        n2 = ops.launch_count()
+        assert torch.equal(a, b) and (n2 - n1) == (n1 - n0) - 3      # no re-pack (2 kernels), no offset kernel
+        e.add_(0.5)                                                    # same storage, new values
+        c = model.run_mlp(x, d, None, e.unsqueeze(0), "bf16x3")
+        assert float((c[:, :3] - a[:, :3]).abs().max()) > 1e-3 and torch.equal(c[:, 3], a[:, 3])
+        fresh = model.run_mlp(x, d, None, e.clone().unsqueeze(0), "bf16x3")
+        assert torch.equal(fresh, c)
+        saved = model.appearance_projection.bias.clone()
+        model.appearance_projection.bias.add_(0.25)                   # weights change -> new packed image -> offsets recomputed
+        w = model.run_mlp(x, d, None, e.unsqueeze(0), "bf16x3")
+        model.appearance_projection.bias.copy_(saved)
+        back = model.run_mlp(x, d, None, e.unsqueeze(0), "bf16x3")
+    assert float((w[:, :3] - c[:, :3]).abs().max()) > 1e-4 and torch.equal(back, c)
