@@ -92,15 +92,16 @@ SIGNATURES = {
 }
 
 
-def build(verbose: bool = False) -> str:
-    """Compile the CUDA sources for sm_100a (nvcc cross-compiles without a GPU) and return the .so path."""
-    proc = subprocess.run(["make", "-C", CSRC, "-j", str(min(8, os.cpu_count() or 1))],
-                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+def build(verbose: bool = False, profile: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a (nvcc cross-compiles without a GPU) and return the .so path.
+    profile=True builds the separate profiling library (`make PROFILE=1`) that scripts/ load with NERFW_PROFILE_LIB=1."""
+    cmd = ["make", "-C", CSRC, "-j", str(min(8, os.cpu_count() or 1))] + (["PROFILE=1"] if profile else [])
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:
         print(proc.stdout)
     if proc.returncode != 0:
-        raise RuntimeError("building libnerfw_sm100.so failed (see output above)")
-    return LIB_PATH
+        raise RuntimeError("building libnerfw_sm100%s.so failed (see output above)" % ("_profile" if profile else ""))
+    return os.path.join(_HERE, "libnerfw_sm100_profile.so") if profile else os.path.join(_HERE, "libnerfw_sm100.so")
 
 
 _lib = None

@@ -1,5 +1,7 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the kernels' profiling switches exist only in the profiling build (make -C csrc PROFILE=1): load that library
+os.environ.setdefault("NERFW_PROFILE_LIB", "1")
 sys.path.insert(0, os.path.join(ROOT, "depth-aware-shader-effects-for-nerf_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch, nerfw, nerfw_oracle as orc
 from config import Config
