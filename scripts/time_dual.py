@@ -1,0 +1,28 @@
+"""Fine-pass MLP launch (640 000 rays x 128 depths) in the single-pass modes: two-tile kernel (default) vs one-tile kernel."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "depth-aware-shader-effects-for-nerf_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import torch, nerfw, nerfw_oracle as orc
+from config import Config
+from nerfw import ops
+m = nerfw.NeRF(Config()); m.load_state_dict(orc.make_state_dict(0)); m = m.cuda().eval()
+emb = torch.randn(1, 32).cuda()
+g = torch.Generator(device="cuda").manual_seed(0)
+b, n = 640000, 128
+o = torch.tensor([0.0, 0.0, 4.0], device="cuda").expand(b, 3).contiguous()
+d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda", generator=g) * 0.3 + torch.tensor([0.0, 0.0, -1.0], device="cuda"), dim=-1)
+z = torch.sort(torch.rand(b, n, device="cuda", generator=g) * 4 + 2, dim=-1).values
+ws, packed = m.kernel_state()[2], m.packed_weights()
+for mode in ("fp16", "bf16"):
+    mid = nerfw.models.resolve_mode(mode)
+    for single in (True, False, True, False):
+        for _ in range(2):
+            raw = ops.mlp_fwd(ws, packed, o, d, z, emb, mid, single_tile=single)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            raw = ops.mlp_fwd(ws, packed, o, d, z, emb, mid, single_tile=single)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"{mode} {'one-tile' if single else 'two-tile'}: {ms:.2f} ms, {b * n * 1063936 / ms / 1e9:.0f} TFLOP/s algorithmic")
