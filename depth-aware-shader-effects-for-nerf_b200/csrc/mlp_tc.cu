@@ -489,333 +489,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Single-pass modes (bf16 / fp16), TWO sample tiles in flight per CTA.
-//
-// Within one tile the layers are serial: layer l+1 needs every output column of layer l, so between the last MMA of a layer
-// and the first MMA of the next the tensor pipe waits for the accumulator to be drained, loaded by the epilogue warps
-// (tcgen05.ld) and for the first operand granule to be written back (~1 000 cycles per layer, section 4 of DESIGN.md).
-// The single-pass modes leave 128 tensor-memory columns free (no lo operand), enough for a second OPERAND region but not
-// for a second accumulator.  So two tiles X and Y share the accumulator columns [0,256) and alternate layer by layer:
-//     MMA:       X.l   Y.l   X.l+1   Y.l+1  ...          epilogue:   X.l   Y.l   X.l+1  ...
-// While the epilogue warps turn X's accumulator into X's next operand (columns [256,384)), the tensor pipe already runs
-// Y's layer from Y's operand region ([384,512)), which was finished during X's MMAs: the MMA thread never waits for an
-// operand, only for the accumulator hand-back (drain + load).  The direction-layer / rgb-head tail of one tile and the
-// encodings overlap with the other tile's MMAs in the same way.  Weight chunks are streamed once per tile as before (both
-// tiles are in the same layer at different times); encodings: one position and one direction tile per slot.
-constexpr uint32_t SM_SIG2 = SM_TOTAL;                    // second slot's density partial sums [4][128] floats
-constexpr uint32_t SM_RGB2 = SM_SIG2 + 4 * TM * 4;        // second slot's rgb logit partial sums [4][128] float4
-constexpr size_t SMEM_BYTES_DUAL = SM_RGB2 + 4 * TM * 16 + 1024;
-static_assert(SMEM_BYTES_DUAL <= 232448, "dual-tile forward kernel: shared memory over the 227 KB limit");
-
-template <bool F16, bool SIGMA>
-__global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_dual_kernel(const uint8_t* __restrict__ packed, SampleSource src,
-                                                                      const float4* __restrict__ app_off, int64_t n_total,
-                                                                      float4* __restrict__ raw, uint32_t* __restrict__ masks,
-                                                                      size_t f16_offset) {
-  constexpr bool sigma_only = SIGMA;
-  constexpr int n_steps = sigma_only ? NERFW_LAYERS : NERFW_LAYERS + 1;          // trunk layers (+ direction layer)
-  extern __shared__ uint8_t smem_dyn[];
-  uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int STAGES = NSTAGES;
-  struct RingPipe {
-    int stage = 0;
-    uint32_t phase = 0;
-    __device__ __forceinline__ void advance() {
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
-  };
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + SM_BAR);
-  uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;
-  uint64_t* acc_free = acc_full + 1;
-  uint64_t* a_kb = acc_free + 1;        // [2][4]: K block kb of slot p's next operand written
-  uint64_t* pe_ready = a_kb + 8;        // [2]: slot p's position tile written
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM_TMEMPTR);
-  float* vec = reinterpret_cast<float*>(sm + SM_VEC);
-  // first weight chunk of every step: layer 0: 1 chunk; layers 1-3: 4; layer 4: 5 (skip); layers 5-7: 4; direction layer: 5
-  constexpr int CHUNK0[11] = {0, 1, 5, 9, 13, 18, 22, 26, 30, 35, 35};
-
-  if (warp == F_PRODUCER_WARP && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_free, F_EPI_WARPS);
-    for (int i = 0; i < 8; ++i) mbar_init(&a_kb[i], F_EPI_WARPS);
-    for (int i = 0; i < 2; ++i) mbar_init(&pe_ready[i], F_EPI_WARPS);
-    fence_mbar_init();
-  }
-  if (warp == F_MMA_WARP) tmem_alloc<512>(tmem_ptr);
-  if (warp < F_EPI_WARPS) {
-    const float* gv = reinterpret_cast<const float*>(packed + W_BYTES);
-    for (int i = tid; i < V_FLOATS; i += F_EPI_THREADS) vec[i] = __ldg(gv + i);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const int64_t ntiles = (n_total + TM - 1) / TM;
-  const int64_t G = gridDim.x;
-  // slot p of pair i works on tile blockIdx.x + (2 i + p) G; a pair's second tile may lie past the end (then only slot 0 runs)
-
-  if (warp == F_PRODUCER_WARP) {
-    // ===================== weight producer: per step, the layer's chunks once per live slot =====================
-    if (lane == 0) {
-      RingPipe p;
-      for (int64_t t0 = blockIdx.x; t0 < ntiles; t0 += 2 * G) {
-        const int nslots = (t0 + G < ntiles) ? 2 : 1;
-        for (int step = 0; step < n_steps; ++step) {
-          for (int slot = 0; slot < nslots; ++slot) {
-            for (int c = CHUNK0[step]; c < CHUNK0[step + 1]; ++c) {
-              const uint32_t sz = c < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
-              mbar_wait(&empty[p.stage], p.phase ^ 1);
-              mbar_arrive_expect_tx(&full[p.stage], sz);
-              const uint8_t* srcw = F16 ? packed + f16_offset + chunk_offset_f16(c) : packed + chunk_offset(c);
-              bulk_g2s(sm + SM_RING + p.stage * BIG_CHUNK, srcw, sz, &full[p.stage]);
-              p.advance();
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == F_MMA_WARP) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      RingPipe p;
-      const uint32_t idesc256 = F16 ? idesc_f16(128, 256) : idesc_bf16(128, 256);
-      const uint32_t idesc128 = F16 ? idesc_f16(128, 128) : idesc_bf16(128, 128);
-      const uint32_t ring = smem_u32(sm + SM_RING);
-      const uint32_t d_acc = tmem + COL_ACC;
-      auto kblock = [&](bool from_tmem, uint64_t a, uint32_t idesc, int ksteps, bool first) {
-        mbar_wait(&full[p.stage], p.phase);
-        tc_fence_after();
-        const uint64_t b = smem_desc_sw128(ring + p.stage * BIG_CHUNK);
-        for (int k = 0; k < ksteps; ++k) {
-          const uint32_t accf = (first && k == 0) ? 0u : 1u;
-          if (from_tmem) mma_ts(d_acc, (uint32_t)a + 8 * k, b + 2 * k, idesc, accf);
-          else mma_ss(d_acc, a + 2 * k, b + 2 * k, idesc, accf);
-        }
-        mma_commit(&empty[p.stage]);
-        p.advance();
-      };
-      const uint64_t pex0 = smem_desc_sw128(smem_u32(sm + SM_PEX_HI)), pex1 = smem_desc_sw128(smem_u32(sm + SM_PEX_LO));
-      const uint64_t ped0 = smem_desc_sw128(smem_u32(sm + SM_PED_HI)), ped1 = smem_desc_sw128(smem_u32(sm + SM_PED_LO));
-      uint32_t ph_free = 0, ph_pe = 0, ph_kb = 0;   // bit `slot` = phase of the slot's barriers
-      auto wait_bar = [&](uint64_t* bar, uint32_t phase) {
-        mbar_wait(bar, phase);
-        tc_fence_after();
-      };
-      for (int64_t t0 = blockIdx.x; t0 < ntiles; t0 += 2 * G) {
-        const int nslots = (t0 + G < ntiles) ? 2 : 1;
-        for (int step = 0; step < n_steps; ++step) {
-          for (int slot = 0; slot < nslots; ++slot) {
-            wait_bar(acc_free, ph_free);           // the previous step's accumulator (the other slot's) sits in registers
-            ph_free ^= 1;
-            const uint64_t pex = slot ? pex1 : pex0;
-            const uint32_t a_op = tmem + (slot ? COL_ALO : COL_AHI);
-            if (step == 0) {
-              wait_bar(&pe_ready[slot], (ph_pe >> slot) & 1u);
-              ph_pe ^= 1u << slot;
-              kblock(false, pex, idesc256, 4, true);
-            } else {
-              const bool dir = step == NERFW_LAYERS;
-              for (int kb = 0; kb < 4; ++kb) {
-                wait_bar(&a_kb[slot * 4 + kb], (ph_kb >> slot) & 1u);
-                kblock(true, a_op + 32 * kb, dir ? idesc128 : idesc256, 4, kb == 0);
-              }
-              ph_kb ^= 1u << slot;
-              if (step == NERFW_SKIP) kblock(false, pex, idesc256, 4, false);
-              if (dir) kblock(false, slot ? ped1 : ped0, idesc128, 2, false);
-            }
-            mma_commit(acc_full);
-          }
-        }
-      }
-    }
-  } else {
-    // ===================== encoders + epilogues (16 warps, thread <-> sample row x column quarter) ==========
-    const uint32_t quad = warp & 3, cq = warp >> 2;
-    const uint32_t row = quad * 32 + lane;
-    const uint32_t tlane = tmem + ((quad * 32) << 16);
-    uint32_t acc_phase = 0;
-    auto pex_of = [&](int slot) { return sm + (slot ? SM_PEX_LO : SM_PEX_HI); };
-    auto ped_of = [&](int slot) { return sm + (slot ? SM_PED_LO : SM_PED_HI); };
-    auto sig_of = [&](int slot) { return reinterpret_cast<float*>(sm + (slot ? SM_SIG2 : SM_SIG)); };
-    auto rgb_of = [&](int slot) { return reinterpret_cast<float4*>(sm + (slot ? SM_RGB2 : SM_RGB)); };
-    mbar_arrive_warp(acc_free);   // the accumulator starts out free
-    auto encode_pos = [&](int slot, int64_t t) {
-      if (cq < 2) {
-        const int64_t sr = t * TM + row;
-        float x[3] = {0.f, 0.f, 0.f};
-        if (sr < n_total) src.position(sr, x);
-        float v[32];
-        if (cq == 0) {
-          pos_features32<0, true>(x, v);
-          store_features32<false, F16>(pex_of(slot), pex_of(slot), row, 0, v);
-        } else {
-          pos_features32<1, true>(x, v);
-          store_features32<false, F16>(pex_of(slot), pex_of(slot), row, 32, v);
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive_warp(&pe_ready[slot]);
-    };
-    auto encode_dir = [&](int slot, int64_t t) {
-      if (cq == 2) {
-        const int64_t sr = t * TM + row;
-        float d[3] = {0.f, 0.f, 0.f};
-        if (sr < n_total) src.direction(sr, d);
-        float v[32];
-        dir_features32<true>(d, v);
-        store_features32<false, F16>(ped_of(slot), ped_of(slot), row, 0, v);
-        fence_proxy_async_smem();   // ordered before this warp's later a_kb arrivals, which the MMA thread waits on
-      }
-    };
-    if ((int64_t)blockIdx.x < ntiles) encode_pos(0, blockIdx.x);
-    if ((int64_t)blockIdx.x + G < ntiles) encode_pos(1, blockIdx.x + G);
-    for (int64_t t0 = blockIdx.x; t0 < ntiles; t0 += 2 * G) {
-      const int nslots = (t0 + G < ntiles) ? 2 : 1;
-      float sig0 = 0.f, sig1 = 0.f;
-      // ---- trunk epilogues, the two slots alternating: acc -> bias, ReLU -> operand of the slot's next layer ----
-      for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
-#pragma unroll 1
-        for (int slot = 0; slot < nslots; ++slot) {
-          const int64_t tile = t0 + slot * G;
-          mbar_wait(acc_full, acc_phase);
-          acc_phase ^= 1;
-          tc_fence_after();
-          const float* bias = vec + V_PTSB + layer * 256;
-          uint32_t r[4][16];
-#pragma unroll
-          for (int kb = 0; kb < 4; ++kb) tmem_ld16(tlane + COL_ACC + cq * 64 + kb * 16, r[kb]);
-          tmem_wait_ld();
-          tc_fence_before();
-          mbar_arrive_warp(acc_free);      // the other slot's MMAs may start
-          float sg = slot ? sig1 : sig0;
-          const uint32_t a_col = slot ? COL_ALO : COL_AHI;
-          if (sigma_only && layer == NERFW_LAYERS - 1) {
-            // nobody consumes layer 7's activations as an operand: only the density head's dot product
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb) {
-              const uint32_t col = cq * 64 + kb * 16;
-#pragma unroll
-              for (int e = 0; e < 16; ++e)
-                sg = fmaf(fmaxf(__fadd_rn(__uint_as_float(r[kb][e]), bias[col + e]), 0.f), vec[V_DENW + col + e], sg);
-            }
-          } else {
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb) {
-              const uint32_t col = cq * 64 + kb * 16;         // accumulator column = output feature
-              const uint32_t apos = (kb * 64 + cq * 16) >> 1;  // operand position: granule kb of quarter cq (kperm_feature)
-              const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-              uint32_t ph[8];
-              float a[16];
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 bb = b4[j4];
-                unpack2f(add2(pack2(r[kb][4 * j4], r[kb][4 * j4 + 1]), pack2f(bb.x, bb.y)), a[4 * j4], a[4 * j4 + 1]);
-                unpack2f(add2(pack2(r[kb][4 * j4 + 2], r[kb][4 * j4 + 3]), pack2f(bb.z, bb.w)), a[4 * j4 + 2], a[4 * j4 + 3]);
-                ph[2 * j4] = F16 ? relu_pack_f16x2(a[4 * j4], a[4 * j4 + 1]) : relu_pack_bf16x2(a[4 * j4], a[4 * j4 + 1]);
-                ph[2 * j4 + 1] = F16 ? relu_pack_f16x2(a[4 * j4 + 2], a[4 * j4 + 3]) : relu_pack_bf16x2(a[4 * j4 + 2], a[4 * j4 + 3]);
-              }
-              tmem_st8(tlane + a_col + apos, ph);
-              if (masks) {  // 16 ReLU gates of this slice = one half of gate word col / 32
-                uint32_t bits = 0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) bits |= (a[j] > 0.f ? 1u : 0u) << j;
-                reinterpret_cast<unsigned short*>(masks)[2 * mask_index(tile, layer, row, 0, (int)(col >> 5)) + ((col >> 4) & 1)] = (unsigned short)bits;
-              }
-              if (layer == NERFW_LAYERS - 1) {
-                const float4* w4 = reinterpret_cast<const float4*>(vec + V_DENW + col);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                  const float4 ww = w4[j4];
-                  sg = fmaf(fmaxf(a[4 * j4], 0.f), ww.x, sg); sg = fmaf(fmaxf(a[4 * j4 + 1], 0.f), ww.y, sg);
-                  sg = fmaf(fmaxf(a[4 * j4 + 2], 0.f), ww.z, sg); sg = fmaf(fmaxf(a[4 * j4 + 3], 0.f), ww.w, sg);
-                }
-              }
-              tmem_wait_st();
-              tc_fence_before();
-              mbar_arrive_warp(&a_kb[slot * 4 + kb]);
-            }
-          }
-          if (slot) sig1 = sg; else sig0 = sg;
-          if (layer == NERFW_SKIP + 1) {
-            // the skip layer has consumed this slot's position tile: encode the slot's direction tile and the position
-            // tile of the slot's NEXT sample tile while the tensor pipe works on the other slot
-            if (!sigma_only) encode_dir(slot, tile);
-            if (tile + 2 * G < ntiles) encode_pos(slot, tile + 2 * G);
-          }
-          if (layer == NERFW_LAYERS - 1) {
-            sig_of(slot)[cq * TM + row] = sg;
-            if (sigma_only) {
-              named_bar_sync(1, F_EPI_THREADS);
-              const int64_t s = tile * TM + row;
-              if (cq == 0 && s < n_total) {
-                const float* sp = sig_of(slot);
-                const float v = (sp[row] + sp[TM + row]) + (sp[2 * TM + row] + sp[3 * TM + row]) + vec[V_DENB];
-                raw[s] = make_float4(0.f, 0.f, 0.f, fmaxf(v, 0.f));
-              }
-            }
-          }
-        }
-      }
-      if (sigma_only) continue;
-      // ---- direction-layer epilogue + rgb head (src/models.py:141-160), slot by slot ----
-#pragma unroll 1
-      for (int slot = 0; slot < nslots; ++slot) {
-        const int64_t tile = t0 + slot * G;
-        const int64_t s = tile * TM + row;
-        const bool live = s < n_total;
-        mbar_wait(acc_full, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        float p3[3] = {0.f, 0.f, 0.f};
-        {
-          const uint32_t col = cq * 32;
-          uint32_t r[32];
-          tmem_ld32(tlane + COL_ACC + col, r);
-          tmem_wait_ld();
-          tc_fence_before();
-          mbar_arrive_warp(acc_free);   // the other slot's direction layer / the next pair's layer 0 may start
-          uint32_t bits = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float hv = fmaxf(__uint_as_float(r[j]) + vec[V_DIRB + col + j], 0.f);
-            bits |= (hv > 0.f ? 1u : 0u) << j;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv, vec[V_RGBW + c * 128 + col + j], p3[c]);
-          }
-          if (masks) masks[mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))] = bits;
-        }
-        float4* rgb_part = rgb_of(slot);
-        const float* sp = sig_of(slot);
-        if (cq != 0) rgb_part[cq * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
-        named_bar_sync(1, F_EPI_THREADS);
-        if (cq == 0 && live) {
-          const float4 o1 = rgb_part[TM + row], o2 = rgb_part[2 * TM + row], o3 = rgb_part[3 * TM + row];
-          float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (app_off) off = __ldg(app_off + src.emb_row(s));
-          const float sgm = (sp[row] + sp[TM + row]) + (sp[2 * TM + row] + sp[3 * TM + row]) + vec[V_DENB];
-          float4 o;
-          o.x = 1.0f / (1.0f + expf(-(p3[0] + o1.x + o2.x + o3.x + vec[V_RGBB + 0] + off.x)));
-          o.y = 1.0f / (1.0f + expf(-(p3[1] + o1.y + o2.y + o3.y + vec[V_RGBB + 1] + off.y)));
-          o.z = 1.0f / (1.0f + expf(-(p3[2] + o1.z + o2.z + o3.z + vec[V_RGBB + 2] + off.z)));
-          o.w = fmaxf(sgm, 0.f);
-          raw[s] = o;
-        }
-      }
-    }
-  }
-  // ---- teardown ----
-  tc_fence_before();
-  __syncthreads();
-  if (warp == F_MMA_WARP) {
-    __syncwarp();
-    tmem_dealloc<512>(tmem);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // Self-test of the primitives: D (128 x N fp32) = A (128 x K bf16) * B (N x K bf16)^T for one CTA.
 // mode 0: A from shared memory (SS); mode 1: A from tensor memory (TS).  K multiple of 64 (<= 256), N multiple of 16.
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat16* __restrict__ A,
@@ -922,10 +595,6 @@ int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSou
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_dual_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES_DUAL));
-    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_dual_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES_DUAL));
-    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_dual_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES_DUAL));
-    NERFW_CUDA(cudaFuncSetAttribute(tc::mlp_tc_fwd_dual_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES_DUAL));
   }
   int64_t ntiles = ceil_div64(n_total, tc::TM);
   int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
@@ -945,16 +614,7 @@ int launch_mlp_tc_fwd(const NerfwWeights& w, const void* packed, const SampleSou
   auto launch = [&](auto kernel) {
     kernel<<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES, stream>>>(pk, src, ao, n_total, out, mk, dbg, timeline, f16_off);
   };
-  auto launch_dual = [&](auto kernel) {
-    kernel<<<(unsigned)grid, tc::F_THREADS, tc::SMEM_BYTES_DUAL, stream>>>(pk, src, ao, n_total, out, mk, f16_off);
-  };
-  // single-pass modes: two tiles in flight per CTA (mlp_tc_fwd_dual_kernel) unless the caller asks for the one-tile kernel
-  // (NERFW_MLP_SINGLE_TILE: the parity tests compare the two bit for bit) or a profiling switch of that kernel is set
-  const bool dual = !x3 && !(mode_flags & NERFW_MLP_SINGLE_TILE) && dbg == 0 && timeline == nullptr;
-  if (dual) {
-    if (sigma_only) { if (f16) launch_dual(tc::mlp_tc_fwd_dual_kernel<true, true>); else launch_dual(tc::mlp_tc_fwd_dual_kernel<false, true>); }
-    else { if (f16) launch_dual(tc::mlp_tc_fwd_dual_kernel<true, false>); else launch_dual(tc::mlp_tc_fwd_dual_kernel<false, false>); }
-  } else if (sigma_only) {
+  if (sigma_only) {
     if (x3) launch(tc::mlp_tc_fwd_kernel<true, false, true>);
     else if (f16) launch(tc::mlp_tc_fwd_kernel<false, true, true>);
     else launch(tc::mlp_tc_fwd_kernel<false, false, true>);

@@ -306,14 +306,13 @@ def pack_weights(params, out: Optional[torch.Tensor] = None, device=None) -> tor
 
 def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: torch.Tensor, z: Optional[torch.Tensor],
             emb: Optional[torch.Tensor], mode: int, want_masks: bool = False, sigma_only: bool = False,
-            app_ws: Optional[list] = None, single_tile: bool = False):
+            app_ws: Optional[list] = None):
     """raw (S,4) = (r,g,b,sigma).  p,d: (B,3) rays with z (B,N), or (S,3) samples with z None.
     want_masks (tensor-core modes): also return the ReLU gate words for nerfw_mlp_bwd_tc -> (raw, masks).
     sigma_only (tensor-core modes, inference): NERFW_MLP_SIGMA_ONLY -- raw = (0, 0, 0, sigma), direction layer skipped.
     app_ws: a one-element list the caller keeps for launches that share weights AND embedding rows (the coarse and fine
     launch of one render; the chunks of one frame): the first launch stores its workspace (holding the per-row rgb-logit
-    offsets) in it, later ones pass NERFW_MLP_APP_CACHED and skip the offset kernel.
-    single_tile: NERFW_MLP_SINGLE_TILE -- the one-tile-in-flight kernel instead of the default two-tile one (same bits)."""
+    offsets) in it, later ones pass NERFW_MLP_APP_CACHED and skip the offset kernel."""
     dev = p.device
     n_rays = p.shape[0]
     n_samples = z.shape[1] if z is not None else 1
@@ -322,7 +321,7 @@ def mlp_fwd(params: dict, packed: Optional[torch.Tensor], p: torch.Tensor, d: to
     emb_rows = 0
     if emb is not None:
         emb_rows = emb.shape[0]
-    flags = int(mode) | (0x100 if sigma_only and int(mode) != 0 else 0) | (0x400 if single_tile else 0)
+    flags = int(mode) | (0x100 if sigma_only and int(mode) != 0 else 0)
     wbytes = _mlp_workspace_bytes(n_rays, emb_rows)
     stream = _stream()
     # re-use only on the stream that wrote the offsets (stream order is what makes them visible to this launch)

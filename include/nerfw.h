@@ -50,9 +50,6 @@ enum {
  * nerfw_mlp_fwd call wrote for the SAME embedding rows and the SAME weights (the coarse and the fine launch of one render,
  * or consecutive 4096-ray chunks of one frame): the small offset kernel is not launched again. */
 #define NERFW_MLP_APP_CACHED 0x200
-/* OR into `mode` (single-pass tensor-core modes): run the one-tile-in-flight kernel instead of the default two-tile one.
- * Same arithmetic, same bits; exists so that the parity tests can compare the two kernels. */
-#define NERFW_MLP_SINGLE_TILE 0x400
 
 /* Architecture constants the kernels are specialised for (config.py:10-33 defaults). */
 #define NERFW_HIDDEN 256

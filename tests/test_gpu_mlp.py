@@ -351,34 +351,3 @@ def test_appearance_offsets_are_cached_per_embedding_and_weights(cuda_model):
         model.appearance_projection.bias.copy_(saved)
         back = model.run_mlp(x, d, None, e.unsqueeze(0), "bf16x3")
     assert float((w[:, :3] - c[:, :3]).abs().max()) > 1e-4 and torch.equal(back, c)
-
-
-@pytest.mark.parametrize("mode", ["fp16", "bf16"])
-def test_two_tile_forward_kernel_bitwise_equals_one_tile_kernel(cuda_model, mode):
-    """The default single-pass forward kernel keeps two sample tiles in flight per CTA (shared accumulator, one operand
-    region per tile).  Same arithmetic in the same order as the one-tile kernel (NERFW_MLP_SINGLE_TILE): identical bits --
-    outputs, ReLU gate words, sigma-only form -- at tile counts that leave a CTA with 1, 2, an odd number and many
-    tiles, ragged last tiles, with and without an embedding."""
-    import nerfw
-    from nerfw import ops
-    model, emb = cuda_model
-    ws = model.kernel_state()[2]
-    packed = model.packed_weights()
-    mode_id = nerfw.models.resolve_mode(mode)
-    g = torch.Generator(device="cuda").manual_seed(21)
-    for b, n in ((1, 1), (100, 128), (149, 128), (296, 128), (297, 129), (445, 127), (3000, 192)):
-        o = torch.randn(b, 3, device="cuda", generator=g)
-        d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda", generator=g), dim=-1)
-        z = torch.sort(torch.rand(b, n, device="cuda", generator=g) * 4 + 2, dim=-1).values
-        e = emb.reshape(1, -1) if b % 2 else None
-        want, wmask = ops.mlp_fwd(ws, packed, o, d, z, e, mode_id, want_masks=True, single_tile=True)
-        got, gmask = ops.mlp_fwd(ws, packed, o, d, z, e, mode_id, want_masks=True)
-        assert torch.equal(got, want), (b, n)
-        # gate words: [tile][layer 0..8][row][8 words]; the direction layer (8) only writes words 0, 1, 4, 5
-        gm, wm = gmask.view(torch.int32).view(-1, 9, 128, 8), wmask.view(torch.int32).view(-1, 9, 128, 8)
-        assert torch.equal(gm[:, :8], wm[:, :8]) and torch.equal(gm[:, 8][..., [0, 1, 4, 5]], wm[:, 8][..., [0, 1, 4, 5]]), (b, n)
-        s_want = ops.mlp_fwd(ws, packed, o, d, z, e, mode_id, sigma_only=True, single_tile=True)
-        s_got = ops.mlp_fwd(ws, packed, o, d, z, e, mode_id, sigma_only=True)
-        assert torch.equal(s_got, s_want) and torch.equal(s_got[:, 3], want[:, 3]), (b, n)
-    again = ops.mlp_fwd(ws, packed, o, d, z, e, mode_id)
-    assert torch.equal(again, got)
