@@ -500,9 +500,13 @@ def run_ours(args):
             issued = ach * (3018496.0 if m == "bf16x3" else 1054464.0) / FLOP_PER_SAMPLE
             roof[label] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": ach / peaks["bf16_tflops_sustained"],
-                           "traffic": 18.9 * float(zz.numel()),
-                           "traffic_source": "constant: 18.9 B/sample from one ncu --set full capture (profiles/r01_ncu_full_mixed.md: "
-                                             "141 MB read + 439 MB written for 30.7 M samples), not re-measured per run",
+                           # DRAM bytes per sample from the round-2 ncu --set full capture of the same kernels on a 160 000-ray crop
+                           # (profiles/r02_ncu_full_mixed.md: bf16x3 launch 48.3 MB read + 110.2 MB written for 10.24 M samples,
+                           # fp16 launch 88.4 + 270.8 MB for 20.48 M; algorithmic 20 B/sample = 4 B depth in + 16 B record out --
+                           # below it because dirty lines still sitting in the 126 MB L2 at kernel end are not counted)
+                           "traffic": (15.5 if m == "bf16x3" else 17.5) * float(zz.numel()),
+                           "traffic_source": "constant per sample from one ncu --set full capture (profiles/r02_ncu_full_mixed.md), "
+                                             "scaled to this launch's sample count; not re-measured per run",
                            "kernel": ("mlp_tc_fwd_kernel<%s%s>" % ({"bf16x3": "X3", "fp16": "F16", "bf16": "BF16"}[m], ",SIGMA" if sig_only else ""))
                            if m != "fp32" else "mlp_ffma_fwd_kernel",
                            "kernel_mode": m, "kernel_ms": kms, "samples_per_launch": int(zz.numel()),

@@ -38,7 +38,7 @@ def test_mse_kernel():
     ar = a.clone().requires_grad_(True)
     want = torch.nn.functional.mse_loss(ar, b)
     want.backward()
-    assert abs(float(loss) - float(want)) <= 1e-6 and maxabs(d, ar.grad) <= 1e-9
+    assert abs(float(loss) - float(want.detach())) <= 1e-6 and maxabs(d, ar.grad) <= 1e-9
 
 
 def test_trainer_step_matches_torch_loop(state_dict, oracle):
@@ -249,7 +249,7 @@ def test_reuse_coarse_training_gradients_equal_two_pass(cuda_model, oracle, mode
         loss = ((rgb - tgt) ** 2).mean() + ((ex["rgb_coarse"] - tgt) ** 2).mean() + 0.1 * depth.mean() + 0.05 * ex["weights"].sum(1).mean()
         loss.backward()
         grads.append({k: p.grad.clone() for k, p in model.named_parameters()} | {"emb": e.grad.clone()})
-        outs.append((rgb.detach(), depth.detach(), ex["z_vals"], float(loss)))
+        outs.append((rgb.detach(), depth.detach(), ex["z_vals"], float(loss.detach())))
     if mode == "fp32":
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
     tol, tol_cos = (1e-4, 0.999999) if mode == "fp32" else (3e-2, 0.999)
