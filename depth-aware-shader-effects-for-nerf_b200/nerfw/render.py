@@ -70,9 +70,10 @@ def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
 
     `background_color` is accepted and ignored, as in the reference (src/render.py:6).  `t_rand` (B,N) / `u_rand`
     (B,NI) inject the uniforms the reference draws at src/ray_utils.py:80 and :119 (otherwise torch.rand on the device,
-    in that order).  `coarse_rgb`: whether the coarse pass of a hierarchical render also evaluates colour
-    (extras['rgb_coarse']); default: only when gradients are recorded (the training loss uses it) -- for inference the
-    coarse pass only has to place the fine samples, so its direction layer and rgb head are skipped.
+    in that order).  `coarse_rgb` (two-pass form only): whether the coarse pass of a hierarchical render also evaluates
+    colour (extras['rgb_coarse']); default: only when gradients are recorded (the training loss uses it) -- in two-pass
+    inference the coarse pass only has to place the fine samples, so its direction layer and rgb head are skipped.  With
+    coarse re-use (below) the coarse records are part of the result, so colour is always evaluated and returned.
     `reuse_coarse` (default ON for inference with ONE network for both passes -- the only case the reference has,
     src/train.py:30; NERFW_REUSE_COARSE=0 or reuse_coarse=False turns it off): the network's value at a depth does not
     depend on which pass asks, so the fine pass evaluates only the n_importance NEW depths and the coarse pass's
