@@ -46,6 +46,18 @@ def make_linear(scheme):
         elif scheme == "fp16_x2_w1":      # split fp16 activations x fp16 weights (2 MMAs)
             xh, xl = split(x, torch.float16)
             y = (xh.double() + xl.double()) @ rnd(w, torch.float16).double().T
+        elif scheme.startswith("fp16_fp8c"):
+            # main term in fp16, both first-order correction terms in fp8 (kind::f8f6f4 runs at twice the fp16 rate):
+            #   x w ~ x16 w16 + e4m3(lo_x 2^sa) e5m2(w 2^-sa) + e5m2(x 2^-sw) e4m3(lo_w 2^sw),  lo = value - fp16(value)
+            sa, sw = 6, 10
+            if ":" in scheme:
+                sa, sw = (int(v) for v in scheme.split(":")[1:3])
+            f8 = lambda t, dt, lim: t.clamp(-lim, lim).to(dt).to(torch.float32)
+            x16, w16 = rnd(x, torch.float16), rnd(w, torch.float16)
+            lox, low = x - x16, w - w16
+            c1 = f8(lox * 2.0 ** sa, torch.float8_e4m3fn, 448.0).double() @ f8(w * 2.0 ** -sa, torch.float8_e5m2, 57344.0).double().T
+            c2 = f8(x * 2.0 ** -sw, torch.float8_e5m2, 57344.0).double() @ f8(low * 2.0 ** sw, torch.float8_e4m3fn, 448.0).double().T
+            y = x16.double() @ w16.double().T + c1 + c2
         else:
             raise ValueError(scheme)
         return (y + b.double()).float()
