@@ -498,9 +498,22 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         if (cq == 0) {
           dsig_s[row] = ds;
           *reinterpret_cast<float4*>(tsc + (size_t)DLS_BLOCK * BLK + row * 16) = make_float4(dlog[0], dlog[1], dlog[2], ds);
-          if (dl_acc && !src.emb_shared) {  // per-ray embeddings: sum of d logits per ray (<= n_per_ray adds per address)
-            if (live) {
-              float* acc = dl_acc + 4 * src.emb_row(s);
+          if (dl_acc && !src.emb_shared) {  // per-ray embeddings: sum of d logits per ray
+            // the 32 samples of a warp are consecutive: with >= 32 samples per ray they belong to one ray (one warp reduction,
+            // one atomic triple) unless the warp straddles a ray boundary or the end of the batch (per-lane atomics)
+            const int64_t er = live ? src.emb_row(s) : -1;
+            const int64_t er0 = __shfl_sync(0xffffffffu, er, 0);
+            if (__all_sync(0xffffffffu, er == er0)) {
+              float a0 = dlog[0], a1 = dlog[1], a2 = dlog[2];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+              }
+              if (lane == 0 && er0 >= 0) { atomicAdd(dl_acc + 4 * er0, a0); atomicAdd(dl_acc + 4 * er0 + 1, a1); atomicAdd(dl_acc + 4 * er0 + 2, a2); }
+            } else if (live) {
+              float* acc = dl_acc + 4 * er;
               atomicAdd(acc + 0, dlog[0]); atomicAdd(acc + 1, dlog[1]); atomicAdd(acc + 2, dlog[2]);
             }
           } else if (dl_acc) {  // sum of d logits of the shared embedding row: appearance gradients are finished from it
