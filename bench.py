@@ -236,9 +236,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def bench_train_step(nerfw, sd, dev, world, mode, n_rays=4096, steps=6, warmup=2, per_ray_emb=False):
+def bench_train_step(nerfw, sd, dev, world, mode, n_rays=4096, steps=50, warmup=10, per_ray_emb=False):
     """BASELINE.json configs[2]: 4096-ray batch per GPU, coarse+fine forward/backward + Adam, data parallel (one
-    all-reduce of the flat gradient buffer per step when world > 1).  Returns ms per step (max over ranks)."""
+    all-reduce of the flat gradient buffer per step when world > 1).  SURVEY.md 8(d): CUDA-event median of 50 steps after
+    10 warm-up steps, all-reduce inside; `ms_per_step` is that median (max over ranks), `mean_ms_per_step` the mean."""
     from config import Config
     from nerfw.train import Trainer
     m = nerfw.NeRF(Config())
@@ -254,14 +255,17 @@ def bench_train_step(nerfw, sd, dev, world, mode, n_rays=4096, steps=6, warmup=2
     for _ in range(warmup):
         tr.step(o, d, tgt, img, NEAR, FAR, N_COARSE, N_IMPORTANCE, perturb=True, generator=g)
     barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    marks[0].record()
+    for i in range(steps):
         loss = tr.step(o, d, tgt, img, NEAR, FAR, N_COARSE, N_IMPORTANCE, perturb=True, generator=g)
-    e1.record()
+        marks[i + 1].record()
     barrier(world)
-    ms = max_over_ranks(e0.elapsed_time(e1) / steps, world)
-    return {"ms_per_step": ms, "rays_per_gpu": n_rays, "n_gpus": world, "samples": "64+128 (coarse+fine fwd/bwd) + Adam",
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+    ms = max_over_ranks(statistics.median(per_step), world)
+    mean_ms = max_over_ranks(marks[0].elapsed_time(marks[steps]) / steps, world)
+    return {"ms_per_step": ms, "mean_ms_per_step": mean_ms, "timing": f"median of {steps} steps after {warmup} warm-up steps (CUDA events)",
+            "rays_per_gpu": n_rays, "n_gpus": world, "samples": "64+128 (coarse+fine fwd/bwd) + Adam",
             "forward_mode": mode, "backward": "tcgen05 bf16 MLP backward (dgrad fused with forward recompute + MN-major wgrad), composite_bwd",
             "allreduce_bytes": int(tr.flat.grad.numel() * 4) if world > 1 else 0, "final_loss": float(loss)}
 
