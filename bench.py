@@ -266,7 +266,8 @@ def bench_train_step(nerfw, sd, dev, world, mode, n_rays=4096, steps=50, warmup=
     mean_ms = max_over_ranks(marks[0].elapsed_time(marks[steps]) / steps, world)
     return {"ms_per_step": ms, "mean_ms_per_step": mean_ms, "timing": f"median of {steps} steps after {warmup} warm-up steps (CUDA events)",
             "rays_per_gpu": n_rays, "n_gpus": world, "samples": "64+128 (coarse+fine fwd/bwd) + Adam",
-            "forward_mode": mode, "backward": "tcgen05 bf16 MLP backward (dgrad fused with forward recompute + MN-major wgrad), composite_bwd",
+            "forward_mode": mode + (" (under autograd: fp16 in both forward launches; bf16x3 coarse pass is an inference setting)" if mode == "mixed" else ""),
+            "backward": "tcgen05 bf16 MLP backward (dgrad fused with forward recompute + MN-major wgrad), composite_bwd",
             "allreduce_bytes": int(tr.flat.grad.numel() * 4) if world > 1 else 0, "final_loss": float(loss)}
 
 

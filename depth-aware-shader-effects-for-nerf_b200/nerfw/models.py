@@ -27,11 +27,17 @@ DEFAULT_MLP_MODE = os.environ.get("NERFW_MLP_MODE", "mixed")
 MODE_CHOICES = sorted(MODE_NAMES) + ["mixed"]
 
 
-def resolve_mode(mode: Optional[str], role: str = "single") -> int:
-    """mode name (or None = default) -> kernel mode id; role = 'coarse' | 'fine' | 'single' resolves "mixed"."""
+def resolve_mode(mode: Optional[str], role: str = "single", training: bool = False) -> int:
+    """mode name (or None = default) -> kernel mode id; role = 'coarse' | 'fine' | 'single' resolves "mixed".
+
+    "mixed": fine pass fp16; coarse pass bf16x3 for inference -- its weights place the fine samples and the rendered depth
+    is sensitive to that placement -- but fp16 when gradients are recorded: a training step jitters both sample sets anyway
+    (perturb=True: stratified depths and u are random), no gradient flows through the placement, and the backward runs in
+    bf16 either way, so the fp32-parity split would buy nothing there (it costs 0.36 ms of a 5.2 ms step).  A single pass
+    (coarse-only render, bare model call) is bf16x3 in both cases."""
     name = (mode or DEFAULT_MLP_MODE).lower()
     if name == "mixed":
-        name = "fp16" if role == "fine" else "bf16x3"
+        name = "fp16" if (role == "fine" or (role == "coarse" and training)) else "bf16x3"
     if name not in MODE_NAMES:
         raise ValueError(f"mlp_dtype must be one of {MODE_CHOICES}, got {mode!r}")
     return MODE_NAMES[name]

@@ -20,10 +20,11 @@ from .models import NeRF, resolve_mode
 
 def _shade(model: NeRF, o, d, z, emb, mode, role="single", sigma_only=False):
     """(rgb (B,3), depth (B,1), acc (B,1), weights (B,N)) for given depths -- src/render.py:29-80."""
-    mode_id = resolve_mode(mode or model.mlp_mode, role)
     names, tensors, ws = model.kernel_state()[:3]
+    training = torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or (emb is not None and emb.requires_grad))
+    mode_id = resolve_mode(mode or model.mlp_mode, role, training)
     packed = model.packed_weights() if mode_id != 0 else None
-    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or (emb is not None and emb.requires_grad)):
+    if training:
         return RenderFn.apply(mode_id, names, o, d, z, emb, packed, *tensors)
     raw = ops.mlp_fwd(ws, packed, o, d, z, None if emb is None else emb.detach(), mode_id, sigma_only=sigma_only,
                       app_ws=model.app_workspace(emb, packed))
@@ -36,10 +37,11 @@ def _render_reusing_coarse(model: NeRF, o, d, z, emb, mode, n_importance, u_rand
     (ReuseRenderFn) when gradients are being recorded."""
     dev, b = o.device, o.shape[0]
     names, tensors, params = model.kernel_state()[:3]
-    mode_c, mode_f = resolve_mode(mode or model.mlp_mode, "coarse"), resolve_mode(mode or model.mlp_mode, "fine")
+    training = torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or (emb is not None and emb.requires_grad))
+    mode_c, mode_f = resolve_mode(mode or model.mlp_mode, "coarse", training), resolve_mode(mode or model.mlp_mode, "fine", training)
     packed = model.packed_weights() if (mode_c != 0 or mode_f != 0) else None
     ur = u_rand.to(dev).reshape(b, n_importance) if u_rand is not None else torch.rand((b, n_importance), device=dev, generator=generator)
-    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or (emb is not None and emb.requires_grad)):
+    if training:
         rgb, depth, acc, w, rgb_c, depth_c, acc_c, w_c, z_all = ReuseRenderFn.apply(mode_c, mode_f, names, o, d, z, emb, packed,
                                                                                    ur.float().contiguous(), *tensors)
     else:
