@@ -712,6 +712,27 @@ def run_ours(args):
                                    "1e-7, bf16x3 1e-6 relative), the more such flips.  bf16x3 and mixed show the same tail, i.e. the "
                                    "fp16 fine pass adds nothing to it; DESIGN.md section 2"}
 
+    # ---- BASELINE.json configs[0]: the reference's own CPU-runnable case, one 100x100 view, 64 + 128 -----------------------
+    config0 = None
+    if not args.no_cpu_baseline:
+        try:
+            import nerfw_oracle as orc
+            h0, w0, f0, c2w0 = orc.golden_camera()
+            ro0c, rd0c = orc.rays_for_view(h0, w0, f0, c2w0)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                rgb_c0, depth_c0, _ = orc.render_coarse(sd, ro0c, rd0c, NEAR, FAR, N_COARSE, emb=emb, perturb=False)
+            cpu_s = time.perf_counter() - t0           # what the reference executes for this call (its fine branch is `pass`)
+            o0, d0 = nerfw.get_rays(h0, w0, f0, c2w0.to(dev))
+            g_ms = timed(lambda: render(o0, d0, fine_pass=False), 10)
+            g_hier_ms = timed(lambda: render(o0, d0), 10)
+            rgb_g0, depth_g0, _ = render(o0, d0, fine_pass=False)
+            config0 = {"workload": "one 100x100 view, 64 samples as the reference executes it (coarse only), and 64+128 hierarchical",
+                       "cpu_reference_s_coarse_only": cpu_s, "cpu_cores": os.cpu_count(), "gpu_ms_coarse_only": g_ms, "gpu_ms_64_128": g_hier_ms,
+                       "rgb_max_abs": float((rgb_g0.cpu() - rgb_c0).abs().max()), "depth_max_abs": float((depth_g0.cpu() - depth_c0).abs().max())}
+        except Exception as e:  # noqa: BLE001
+            config0 = {"error": repr(e)[:300]}
+
     value = world * n_rays * args.steps / (ms_total * 1e-3) / 1e6
     e2e_val = world * n_rays * args.steps / (e2e_ms * 1e-3) / 1e6
     dominant = max(("fine", "coarse"), key=lambda k: roof[k]["kernel_ms"])
@@ -751,6 +772,7 @@ def run_ours(args):
         "other_modes": other_modes,
         "train_step": train,
         "stress_256_512": stress,
+        "config0_100x100": config0,
         "eager_baseline": eager,
         **legs,
         "cpu_baseline": cpu,

@@ -15,7 +15,7 @@ for k, v in d["roofline_other"].items():
 print("train_step:", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in d["train_step"].items() if k != "backward"})
 for k, v in d["other_modes"].items():
     print(f"  {k}:", {kk: (round(vv, 3) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk not in ("unit",)})
-for k in ("stress_256_512", "eager_baseline", "strong_one_frame", "spiral_120", "dp_check", "cpu_baseline"):
+for k in ("stress_256_512", "config0_100x100", "eager_baseline", "strong_one_frame", "spiral_120", "dp_check", "cpu_baseline"):
     if d.get(k):
         print(f"{k}:", {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in d[k].items() if kk not in ("partition", "what", "kind", "note")})
 p = d.get("parity_vs_oracle")
