@@ -3,6 +3,12 @@ import json
 import sys
 
 d = json.load(open(sys.argv[1]))
+
+
+def round(v, nd):   # noqa: A001  (4 significant digits, so that 4.4e-6 does not print as 0.0)
+    return float(f"{v:.4g}")
+
+
 print(f"value {d['value']:.3f} {d['unit']}  e2e {d['e2e']['value']:.3f}  ms/step {d['ms_per_step']:.2f}  n_gpus {d['n_gpus']}  "
       f"launches {d['gpu_launches']}  clocks {d['clocks']}")
 r = d["roofline"]
