@@ -594,33 +594,41 @@ def run_ours(args):
         other_modes["mode_fp32"] = {"value": world * n_rays / (ms32 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms32, "mlp_dtype": "fp32"}
     # the reference's own calling pattern: 4096-ray chunks with a device->host copy per chunk
     # (render_aligned_spiral.py:136-155), one frame
-    with torch.no_grad():
-        for j in range(0, 3 * 4096, 4096):
-            render(o_dev[j:j + 4096], d_dev[j:j + 4096])
-        chunk_runs = []
-        for _ in range(3):      # a host-latency-bound loop (157 calls, 314 synchronising copies): best of 3, all reported
-            barrier(world)
-            t0 = time.perf_counter()
-            parts = []
-            for j in range(0, n_rays, 4096):
-                c_rgb, c_depth, _ = render(o_dev[j:j + 4096], d_dev[j:j + 4096])
-                parts.append((c_rgb.cpu(), c_depth.cpu()))
-            barrier(world)
-            chunk_runs.append(max_over_ranks((time.perf_counter() - t0) * 1e3, world))
-        chunk_ms = min(chunk_runs)
-        # host time of one call (no sync inside): what the shim adds per chunk on top of the kernels
-        host_us = 1e9
-        for _ in range(5):       # 20 calls (~220 launches) per burst: the launch queue never fills, so this is host time only
+    def chunk_loop(runs, **kw):
+        with torch.no_grad():
+            for j in range(0, 3 * 4096, 4096):
+                render(o_dev[j:j + 4096], d_dev[j:j + 4096], **kw)
+            chunk_runs = []
+            for _ in range(runs):   # a host-latency-bound loop (157 calls, 314 synchronising copies): best of `runs`, all reported
+                barrier(world)
+                t0 = time.perf_counter()
+                parts = []
+                for j in range(0, n_rays, 4096):
+                    c_rgb, c_depth, _ = render(o_dev[j:j + 4096], d_dev[j:j + 4096], **kw)
+                    parts.append((c_rgb.cpu(), c_depth.cpu()))
+                barrier(world)
+                chunk_runs.append(max_over_ranks((time.perf_counter() - t0) * 1e3, world))
+            # host time of one call (no sync inside): what the shim adds per chunk on top of the kernels
+            host_us = 1e9
+            for _ in range(5):       # 20 calls per burst: the launch queue never fills, so this is host time only
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    render(o_dev[:4096], d_dev[:4096], **kw)
+                host_us = min(host_us, (time.perf_counter() - t0) / 20 * 1e6)
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(20):
-                render(o_dev[:4096], d_dev[:4096])
-            host_us = min(host_us, (time.perf_counter() - t0) / 20 * 1e6)
-        torch.cuda.synchronize()
+        return min(chunk_runs), chunk_runs, host_us
+
+    chunk_ms, chunk_runs, host_us = chunk_loop(3)                 # default: one library call per chunk (nerfw_volume_render)
+    cbc_ms, cbc_runs, cbc_host_us = chunk_loop(2, fused=False)    # the same chunk through the separate entry points
     other_modes["chunked_4096_with_cpu_copy"] = {"value": world * n_rays / (chunk_ms * 1e-3) / 1e6, "unit": "Mrays/s",
                                                  "ms_per_step": chunk_ms, "mlp_mode": mode,
                                                  "calls_per_frame": (n_rays + 4095) // 4096, "runs_ms": chunk_runs,
-                                                 "host_us_per_call_enqueue": host_us}
+                                                 "host_us_per_call_enqueue": host_us,
+                                                 "library_calls_per_chunk": 1,
+                                                 "call_by_call": {"ms_per_step": cbc_ms, "runs_ms": cbc_runs,
+                                                                  "host_us_per_call_enqueue": cbc_host_us,
+                                                                  "library_calls_per_chunk": 9}}
     train = bench_train_step(nerfw, sd, dev, world, mode)
     if mode != "bf16x3":
         train["bf16x3_forward_ms_per_step"] = bench_train_step(nerfw, sd, dev, world, "bf16x3")["ms_per_step"]

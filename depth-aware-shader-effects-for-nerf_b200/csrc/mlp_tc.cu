@@ -140,6 +140,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   const int debug_skip_weights = flags & 1;
   constexpr bool sigma_only = SIGMA;
   constexpr int n_chunks = sigma_only ? N_BIG : N_CHUNKS;
+  // Single-MMA modes (bf16 / fp16) have tensor-pipe time to win at the hand-offs (the split mode issues at the power cap):
+  //  * ENC_FIRST: the K blocks whose A operand is an encoding tile in shared memory (skip part of layer 4, direction part of
+  //    the direction layer) are issued FIRST in their layer -- they need the accumulator but no epilogue output, so they
+  //    run while the previous layer's epilogue is still producing its first operand granule;
+  //  * DIR_ACC: the direction layer accumulates into TMEM columns [384,512) (the A_lo region, unused without the split), so
+  //    layer 0 of the NEXT tile is issued right behind it and the epilogue warps finish that layer 0 -- i.e. restart the
+  //    tensor pipe on layer 1 -- BEFORE they turn to the direction-layer accumulator and the rgb head of the previous tile.
+  constexpr bool ENC_FIRST = !X3;
+  constexpr bool DIR_ACC = !X3 && !SIGMA;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -161,6 +170,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   uint64_t* a_kb = acc_full + 2;
   uint64_t* acc_free = a_kb + 4;
   uint64_t* pe_ready = acc_free + 1;
+  uint64_t* acc2_full = acc_full + 1;   // direction-layer accumulator (DIR_ACC)
+  uint64_t* acc2_free = pe_ready + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + SM_TMEMPTR);
   float* vec = reinterpret_cast<float*>(sm + SM_VEC);
   float* sig_part = reinterpret_cast<float*>(sm + SM_SIG);
@@ -169,6 +180,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   if (warp == F_PRODUCER_WARP && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_free, F_EPI_WARPS);
     for (int i = 0; i < 4; ++i) mbar_init(&a_kb[i], F_EPI_WARPS);
     mbar_init(acc_free, F_EPI_WARPS);
     mbar_init(pe_ready, F_EPI_WARPS);
@@ -195,8 +208,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     if (lane == 0) {
       RingPipe p;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        size_t off = 0;
-        for (int i = 0; i < n_chunks; ++i) {
+        for (int j = 0; j < n_chunks; ++j) {
+          // consumption order of the MMA thread: with ENC_FIRST the encoding chunk of layer 4 / the direction layer leads
+          int i = j;
+          if (ENC_FIRST && j >= 13 && j < 18) i = j == 13 ? 17 : j - 1;
+          if (ENC_FIRST && j >= N_BIG) i = j == N_BIG ? N_CHUNKS - 1 : j - 1;
           const uint32_t sz = i < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
           const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
           for (int v = 0; v < copies; ++v) {
@@ -205,12 +221,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
               mbar_arrive(&full[p.stage]);   // profiling only: reuse whatever the stage holds (results are wrong)
             } else {
               mbar_arrive_expect_tx(&full[p.stage], sz);
-              const uint8_t* srcw = F16 ? packed + f16_offset + chunk_offset_f16(i) : packed + off + (size_t)v * sz;
+              const uint8_t* srcw = F16 ? packed + f16_offset + chunk_offset_f16(i) : packed + chunk_offset(i) + (size_t)v * sz;
               bulk_g2s(sm + RING + p.stage * BIG_CHUNK, srcw, sz, &full[p.stage]);
             }
             p.advance();
           }
-          off += 2ull * sz;
         }
       }
     }
@@ -222,20 +237,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       const uint32_t idesc128 = F16 ? idesc_f16(128, 128) : idesc_bf16(128, 128);
       const uint32_t ring = smem_u32(sm + RING);
       const uint32_t d_acc = tmem + COL_ACC;
+      const uint32_t d_dir = DIR_ACC ? tmem + COL_ALO : d_acc;
       // one 64-wide K block: A (hi[,lo]) x W chunk (hi[,lo]); a_* are either TMEM addresses (TS) or smem descs (SS)
-      auto kblock = [&](bool from_tmem, uint64_t a_hi, uint64_t a_lo, uint32_t idesc, int ksteps, bool first, bool split = X3) {
+      auto kblock = [&](uint32_t d, bool from_tmem, uint64_t a_hi, uint64_t a_lo, uint32_t idesc, int ksteps, bool first, bool split = X3) {
         mbar_wait(&full[p.stage], p.phase);
         tc_fence_after();
         uint64_t b = smem_desc_sw128(ring + p.stage * BIG_CHUNK);
         for (int k = 0; k < ksteps; ++k) {
           uint32_t accf = (first && k == 0) ? 0u : 1u;
-          if (from_tmem) mma_ts(d_acc, (uint32_t)a_hi + 8 * k, b + 2 * k, idesc, accf);
-          else mma_ss(d_acc, a_hi + 2 * k, b + 2 * k, idesc, accf);
+          if (from_tmem) mma_ts(d, (uint32_t)a_hi + 8 * k, b + 2 * k, idesc, accf);
+          else mma_ss(d, a_hi + 2 * k, b + 2 * k, idesc, accf);
         }
         if (split) {
           for (int k = 0; k < ksteps; ++k) {
-            if (from_tmem) mma_ts(d_acc, (uint32_t)a_lo + 8 * k, b + 2 * k, idesc, 1u);
-            else mma_ss(d_acc, a_lo + 2 * k, b + 2 * k, idesc, 1u);
+            if (from_tmem) mma_ts(d, (uint32_t)a_lo + 8 * k, b + 2 * k, idesc, 1u);
+            else mma_ss(d, a_lo + 2 * k, b + 2 * k, idesc, 1u);
           }
         }
         mma_commit(&empty[p.stage]);
@@ -245,8 +261,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           tc_fence_after();
           uint64_t bl = smem_desc_sw128(ring + p.stage * BIG_CHUNK);
           for (int k = 0; k < ksteps; ++k) {
-            if (from_tmem) mma_ts(d_acc, (uint32_t)a_hi + 8 * k, bl + 2 * k, idesc, 1u);
-            else mma_ss(d_acc, a_hi + 2 * k, bl + 2 * k, idesc, 1u);
+            if (from_tmem) mma_ts(d, (uint32_t)a_hi + 8 * k, bl + 2 * k, idesc, 1u);
+            else mma_ss(d, a_hi + 2 * k, bl + 2 * k, idesc, 1u);
           }
           mma_commit(&empty[p.stage]);
           p.advance();
@@ -256,44 +272,67 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       const uint64_t ped_hi = smem_desc_sw128(smem_u32(sm + PED_HI)), ped_lo = smem_desc_sw128(smem_u32(sm + SM_PED_LO));
       // The epilogue frees the accumulator as soon as it sits in registers and publishes the next A operand one 64-wide
       // K block at a time, so the MMAs of layer l+1 start while most of epilogue l is still running.
-      uint32_t ph_free = 0, ph_pe = 0, ph_kb = 0;
+      uint32_t ph_free = 0, ph_pe = 0, ph_kb = 0, ph_free2 = 0;
       auto wait_bar = [&](uint64_t* bar, uint32_t phase) {
         mbar_wait(bar, phase);
         tc_fence_after();
       };
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int64_t tile = blockIdx.x;
+      // layer 0 of `tile`: position encodings (shared memory) x chunk 0
+      auto layer0 = [&]() {
         wait_bar(pe_ready, ph_pe);
         ph_pe ^= 1;
         NERFW_STAMP(0);
-        for (int layer = 0; layer < NERFW_LAYERS; ++layer) {
-          wait_bar(acc_free, ph_free);
-          ph_free ^= 1;
-          NERFW_STAMP(10 + layer * 8);       // accumulator free seen by the MMA thread
-          if (layer == 0) {
-            kblock(false, pex_hi, pex_lo, idesc256, 4, true);
-          } else {
-            for (int kb = 0; kb < 4; ++kb) {
-              wait_bar(&a_kb[kb], ph_kb);
-              if (kb == 0) NERFW_STAMP(11 + layer * 8);   // first operand K block seen
-              if (kb == 3) NERFW_STAMP(12 + layer * 8);   // last operand K block seen
-              kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc256, 4, kb == 0);
-            }
-            ph_kb ^= 1;
-            if (layer == NERFW_SKIP) kblock(false, pex_hi, pex_lo, idesc256, 4, false);
-          }
-          mma_commit(acc_full);
-          NERFW_STAMP(13 + layer * 8);       // all MMAs of the layer issued
-        }
-        if (sigma_only) continue;
         wait_bar(acc_free, ph_free);
         ph_free ^= 1;
+        NERFW_STAMP(10);                     // accumulator free seen by the MMA thread
+        kblock(d_acc, false, pex_hi, pex_lo, idesc256, 4, true);
+        mma_commit(acc_full);
+        NERFW_STAMP(13);                     // all MMAs of the layer issued
+      };
+      for (; tile < ntiles; tile += gridDim.x) {
+        // DIR_ACC: layer 0 of every tile but the first was issued behind the previous tile's direction layer
+        if (!DIR_ACC || tile == (int64_t)blockIdx.x) layer0();
+        for (int layer = 1; layer < NERFW_LAYERS; ++layer) {
+          wait_bar(acc_free, ph_free);
+          ph_free ^= 1;
+          NERFW_STAMP(10 + layer * 8);
+          const bool skip = layer == NERFW_SKIP;
+          if (ENC_FIRST && skip) kblock(d_acc, false, pex_hi, pex_lo, idesc256, 4, true);
+          for (int kb = 0; kb < 4; ++kb) {
+            wait_bar(&a_kb[kb], ph_kb);
+            if (kb == 0) NERFW_STAMP(11 + layer * 8);   // first operand K block seen
+            if (kb == 3) NERFW_STAMP(12 + layer * 8);   // last operand K block seen
+            kblock(d_acc, true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc256, 4, kb == 0 && !(ENC_FIRST && skip));
+          }
+          ph_kb ^= 1;
+          if (!ENC_FIRST && skip) kblock(d_acc, false, pex_hi, pex_lo, idesc256, 4, false);
+          mma_commit(acc_full);
+          NERFW_STAMP(13 + layer * 8);
+        }
+        if (sigma_only) continue;
+        // direction layer (N = 128): [h (256) | direction encoding (27 -> 32)]
+        if (DIR_ACC) {
+          wait_bar(acc2_free, ph_free2);
+          ph_free2 ^= 1;
+        } else {
+          wait_bar(acc_free, ph_free);
+          ph_free ^= 1;
+        }
+        if (ENC_FIRST) kblock(d_dir, false, ped_hi, ped_lo, idesc128, 2, true, dir_split);
         for (int kb = 0; kb < 4; ++kb) {
           wait_bar(&a_kb[kb], ph_kb);
-          kblock(true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, kb == 0, dir_split);
+          kblock(d_dir, true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, kb == 0 && !ENC_FIRST, dir_split);
         }
         ph_kb ^= 1;
-        kblock(false, ped_hi, ped_lo, idesc128, 2, false, dir_split);
-        mma_commit(acc_full);
+        if (!ENC_FIRST) kblock(d_dir, false, ped_hi, ped_lo, idesc128, 2, false, dir_split);
+        mma_commit(DIR_ACC ? acc2_full : acc_full);
+        NERFW_STAMP(94);                     // direction layer issued
+        if (DIR_ACC && tile + gridDim.x < ntiles) {
+          tile += gridDim.x;                 // (stamps of layer 0 belong to the tile it is part of)
+          layer0();
+          tile -= gridDim.x;
+        }
       }
     }
   } else {
@@ -306,6 +345,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     uint8_t* pex_lo = sm + SM_PEX_LO;
     uint8_t* ped_hi = sm + PED_HI;
     mbar_arrive_warp(acc_free);   // the accumulator starts out free
+    if (DIR_ACC) mbar_arrive_warp(acc2_free);
     // ---- encodings (src/models.py:35-44).  Column quarters 0 / 1 write position features 0..31 / 32..63 of a tile,
     // quarter 2 its direction tile.  They are not on the MMA critical path: the position tile of the NEXT sample tile and
     // the direction tile of the current one are filled in between two trunk epilogues, once the skip layer has consumed
@@ -339,6 +379,68 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         fence_proxy_async_smem();   // ordered before this warp's later a_kb arrivals, which the MMA thread waits on
       }
     };
+    // ---- direction-layer epilogue + rgb head of one tile (src/models.py:141-160).  DIR_ACC: the layer has its own accumulator
+    // and barriers, and the call for tile t is made from inside tile t+1, after its layer-0 epilogue (see the tile loop).
+    uint32_t acc2_phase = 0;
+    auto dir_epilogue = [&](int64_t tile) {
+      const int64_t s = tile * TM + row;
+      const bool live = s < n_total;
+      if (DIR_ACC) {
+        mbar_wait(acc2_full, acc2_phase);
+        acc2_phase ^= 1;
+      } else {
+        mbar_wait(acc_full, acc_phase);
+        acc_phase ^= 1;
+      }
+      tc_fence_after();
+      if (tid == 0) NERFW_STAMP(91);   // direction-layer accumulator complete seen
+      float p3[3] = {0.f, 0.f, 0.f};
+      {
+        const uint32_t col = cq * 32;
+        uint32_t r[32];
+        tmem_ld32(tlane + (DIR_ACC ? COL_ALO : COL_ACC) + col, r);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_warp(DIR_ACC ? acc2_free : acc_free);   // the next direction layer / the next tile's layer 0 may start
+        if (tid == 0) NERFW_STAMP(92);
+        uint32_t bits = 0;
+        // bias and rgb-head rows as 16-byte shared-memory loads (a quarter of the wavefronts of scalar loads: this epilogue
+        // runs next to the MMAs of the following tile's layer 1, which read their B operand through the same pipe)
+        const float4* b4 = reinterpret_cast<const float4*>(vec + V_DIRB + col);
+        const float4* w4 = reinterpret_cast<const float4*>(vec + V_RGBW + col);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bb = b4[j4], wr = w4[j4], wg = w4[32 + j4], wb = w4[64 + j4];
+          const float bj[4] = {bb.x, bb.y, bb.z, bb.w};
+          const float wj[3][4] = {{wr.x, wr.y, wr.z, wr.w}, {wg.x, wg.y, wg.z, wg.w}, {wb.x, wb.y, wb.z, wb.w}};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * j4 + e;
+            float hv = fmaxf(__uint_as_float(r[j]) + bj[e], 0.f);
+            bits |= (hv > 0.f ? 1u : 0u) << j;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv, wj[c][e], p3[c]);
+          }
+        }
+        if (masks) masks[mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))] = bits;
+      }
+      if (cq != 0) rgb_part[cq * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
+      named_bar_sync(1, F_EPI_THREADS);
+      if (cq == 0 && live) {
+        const float4 o1 = rgb_part[TM + row], o2 = rgb_part[2 * TM + row], o3 = rgb_part[3 * TM + row];
+        float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (app_off) off = __ldg(app_off + src.emb_row(s));
+        float sg = (sig_part[row] + sig_part[TM + row]) + (sig_part[2 * TM + row] + sig_part[3 * TM + row]) + vec[V_DENB];
+        float4 o;
+        o.x = 1.0f / (1.0f + expf(-(p3[0] + o1.x + o2.x + o3.x + vec[V_RGBB + 0] + off.x)));
+        o.y = 1.0f / (1.0f + expf(-(p3[1] + o1.y + o2.y + o3.y + vec[V_RGBB + 1] + off.y)));
+        o.z = 1.0f / (1.0f + expf(-(p3[2] + o1.z + o2.z + o3.z + vec[V_RGBB + 2] + off.z)));
+        o.w = fmaxf(sg, 0.f);
+        raw[s] = o;
+      }
+      if (tid == 0) NERFW_STAMP(93);   // tile written
+    };
+    int64_t pending = -1;
     if ((int64_t)blockIdx.x < ntiles) encode_pos(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t s = tile * TM + row;
@@ -422,6 +524,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           if (tid == 0 && kb == 0) NERFW_STAMP(16 + layer * 8);
           if (tid == 0 && kb == 3) NERFW_STAMP(17 + layer * 8);
         }
+        // DIR_ACC: layer 1's first operand block is out and the tensor pipe busy again: now finish the PREVIOUS tile
+        // (its sig_part / direction accumulator are untouched until this tile's layer 7 / direction layer)
+        if (DIR_ACC && layer == 0 && pending >= 0) {
+          dir_epilogue(pending);
+          pending = -1;
+        }
         if (layer == NERFW_SKIP + 1) {
           if (!sigma_only) encode_dir(tile);
           if (tile + gridDim.x < ntiles) encode_pos(tile + gridDim.x);
@@ -438,46 +546,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         continue;
       }
 
-      // ---- direction-layer epilogue + rgb head (src/models.py:141-160) ----
-      mbar_wait(acc_full, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
-      if (tid == 0) NERFW_STAMP(91);   // direction-layer accumulator complete seen
-      float p3[3] = {0.f, 0.f, 0.f};
-      {
-        const uint32_t col = cq * 32;
-        uint32_t r[32];
-        tmem_ld32(tlane + COL_ACC + col, r);
-        tmem_wait_ld();
-        tc_fence_before();
-        mbar_arrive_warp(acc_free);   // the next tile's layer 0 may start
-        if (tid == 0) NERFW_STAMP(92);
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float hv = fmaxf(__uint_as_float(r[j]) + vec[V_DIRB + col + j], 0.f);
-          bits |= (hv > 0.f ? 1u : 0u) << j;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv, vec[V_RGBW + c * 128 + col + j], p3[c]);
-        }
-        if (masks) masks[mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))] = bits;
-      }
-      if (cq != 0) rgb_part[cq * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
-      named_bar_sync(1, F_EPI_THREADS);
-      if (cq == 0 && live) {
-        const float4 o1 = rgb_part[TM + row], o2 = rgb_part[2 * TM + row], o3 = rgb_part[3 * TM + row];
-        float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (app_off) off = __ldg(app_off + src.emb_row(s));
-        float sg = (sig_part[row] + sig_part[TM + row]) + (sig_part[2 * TM + row] + sig_part[3 * TM + row]) + vec[V_DENB];
-        float4 o;
-        o.x = 1.0f / (1.0f + expf(-(p3[0] + o1.x + o2.x + o3.x + vec[V_RGBB + 0] + off.x)));
-        o.y = 1.0f / (1.0f + expf(-(p3[1] + o1.y + o2.y + o3.y + vec[V_RGBB + 1] + off.y)));
-        o.z = 1.0f / (1.0f + expf(-(p3[2] + o1.z + o2.z + o3.z + vec[V_RGBB + 2] + off.z)));
-        o.w = fmaxf(sg, 0.f);
-        raw[s] = o;
-      }
-      if (tid == 0) NERFW_STAMP(93);   // tile written
+      if (DIR_ACC) pending = tile;   // finished inside the next tile (or after the loop)
+      else dir_epilogue(tile);
     }
+    if (DIR_ACC && pending >= 0) dir_epilogue(pending);
   }
   // ---- teardown ----
   tc_fence_before();

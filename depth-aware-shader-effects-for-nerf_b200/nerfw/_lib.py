@@ -35,6 +35,12 @@ class NerfwWeights(C.Structure):
 
 NerfwGrads = NerfwWeights  # same layout (include/nerfw.h)
 
+
+class NerfwRenderOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("rgb", "depth", "acc", "weights", "z_vals", "rgb_coarse", "depth_coarse",
+                                          "acc_coarse", "weights_coarse", "z_coarse")]
+
+
 # name -> (restype, argtypes); mirrors include/nerfw.h one to one
 SIGNATURES = {
     "nerfw_last_error": (C.c_char_p, []),
@@ -77,6 +83,10 @@ SIGNATURES = {
     "nerfw_merge_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nerfw_unmerge_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    "nerfw_volume_render_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int, C.c_int64]),
+    "nerfw_volume_render": (C.c_int, [C.POINTER(NerfwWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int,
+                                       C.c_int, C.POINTER(NerfwRenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nerfw_max_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nerfw_fog": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                             C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),

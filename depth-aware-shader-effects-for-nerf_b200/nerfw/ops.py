@@ -404,6 +404,58 @@ def composite_bwd(raw: torch.Tensor, z: torch.Tensor, d_rgb: torch.Tensor, d_dep
     return d_raw
 
 
+# ------------------------------------------------------------------------------------------------ whole inference path
+_VR_WS_BYTES: dict = {}
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+def volume_render_fused(params, packed: Optional[torch.Tensor], rays_o: torch.Tensor, rays_d: torch.Tensor,
+                        ztab: torch.Tensor, t_rand: Optional[torch.Tensor], n_importance: int,
+                        u_rand: Optional[torch.Tensor], emb: Optional[torch.Tensor], mode_coarse: int, mode_fine: int) -> dict:
+    """nerfw_volume_render: the inference form of src/render.py:5-97 in one library call (same kernels, same order, same
+    bits as the call-by-call path).  rays_o / rays_d (B,3) fp32 contiguous CUDA, rays_d not normalised.  Returns the
+    outputs as views of ONE allocation: rgb, depth, acc, weights, z_vals [+ *_coarse, z_coarse when n_importance > 0]."""
+    dev = rays_o.device
+    b = rays_o.shape[0]
+    n = ztab.numel()
+    ni = int(n_importance)
+    emb_rows = emb.shape[0] if emb is not None else 0
+    key = (b, n, ni, emb_rows)
+    wbytes = _VR_WS_BYTES.get(key)
+    if wbytes is None:
+        if len(_VR_WS_BYTES) > 4096:
+            _VR_WS_BYTES.clear()
+        wbytes = _VR_WS_BYTES[key] = int(lib().nerfw_volume_render_workspace_bytes(b, n, ni, emb_rows))
+    # one output allocation; every section starts on a 16-byte boundary
+    sizes = [("rgb", 3 * b, (b, 3)), ("depth", b, (b, 1)), ("acc", b, (b, 1)), ("weights", b * (n + ni), (b, n + ni)),
+             ("z_vals", b * (n + ni), (b, n + ni))]
+    if ni > 0:
+        sizes += [("rgb_coarse", 3 * b, (b, 3)), ("depth_coarse", b, (b, 1)), ("acc_coarse", b, (b, 1)),
+                  ("weights_coarse", b * n, (b, n)), ("z_coarse", b * n, (b, n))]
+    total = 0
+    offs = []
+    for _, cnt, _shape in sizes:
+        offs.append(total)
+        total += _pad4(cnt)
+    flat = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+    ws_buf = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
+    base = flat.data_ptr()
+    out = _lib.NerfwRenderOut()
+    for (name, _cnt, _shape), off in zip(sizes, offs):
+        setattr(out, name, base + 4 * off)
+    ws = weights_struct(params)
+    ulin = u_table(ni, dev) if ni > 0 else None
+    with _on(dev):
+        check(lib().nerfw_volume_render(C.byref(ws), _ptr(packed), rays_o.data_ptr(), rays_d.data_ptr(), b, ztab.data_ptr(),
+                                        _ptr(t_rand), n, _ptr(ulin), _ptr(u_rand), ni, _ptr(emb), emb_rows, int(mode_coarse),
+                                        int(mode_fine), C.byref(out), ws_buf.data_ptr(), ws_buf.numel(), _stream()))
+    # views are cut after the launches are queued (host time that overlaps the GPU's)
+    return {name: flat[off:off + cnt].view(shape) for (name, cnt, shape), off in zip(sizes, offs)}
+
+
 # ------------------------------------------------------------------------------------------------ training helpers
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
               lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0) -> None:

@@ -64,10 +64,48 @@ def _render_reusing_coarse(model: NeRF, o, d, z, emb, mode, n_importance, u_rand
     return rgb_map, depth_map, extras
 
 
+def _records_gradients(model: NeRF, emb) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    tensors = model.kernel_state()[1]
+    return any(t.requires_grad for t in tensors) or (emb is not None and emb.requires_grad)
+
+
+def _render_fused(model: NeRF, o, d, ztab, tr, n_importance, u_rand, generator, emb, mode, orig_shape, src_dev):
+    """Inference through nerfw_volume_render (one call): single pass (n_importance == 0) or coarse + fine with re-use."""
+    dev, b = o.device, o.shape[0]
+    params = model.kernel_state()[2]
+    hier = n_importance > 0
+    m = mode or model.mlp_mode
+    mode_c = resolve_mode(m, "coarse" if hier else "single", False)
+    mode_f = resolve_mode(m, "fine", False) if hier else mode_c
+    packed = model.packed_weights() if (mode_c != 0 or mode_f != 0) else None
+    ur = None
+    if hier:
+        ur = u_rand.to(dev).reshape(b, n_importance) if u_rand is not None else torch.rand((b, n_importance), device=dev, generator=generator)
+        ur = ur.float().contiguous()
+    if tr is not None:
+        tr = tr.float().contiguous()
+    r = ops.volume_render_fused(params, packed, o, d, ztab, tr, n_importance, ur, None if emb is None else emb.detach(),
+                                mode_c, mode_f)
+    extras = {"weights": r["weights"].unsqueeze(-1), "z_vals": r["z_vals"], "acc": r["acc"]}
+    if hier:
+        extras.update({"rgb_coarse": r["rgb_coarse"].reshape(*orig_shape[:-1], 3),
+                       "depth_coarse": r["depth_coarse"].reshape(*orig_shape[:-1], 1), "acc_coarse": r["acc_coarse"],
+                       "weights_coarse": r["weights_coarse"].unsqueeze(-1), "z_vals_coarse": r["z_coarse"]})
+    rgb_map = r["rgb"].reshape(*orig_shape[:-1], 3)
+    depth_map = r["depth"].reshape(*orig_shape[:-1], 1)
+    if src_dev != dev:
+        rgb_map, depth_map = rgb_map.to(src_dev), depth_map.to(src_dev)
+        extras = {k: v.to(src_dev) for k, v in extras.items()}
+    return rgb_map, depth_map, extras
+
+
 def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
                   appearance_embedding=None, background_color=None, perturb=True, *,
                   mlp_dtype: Optional[str] = None, fine_pass: Optional[bool] = None, generator=None,
-                  t_rand=None, u_rand=None, coarse_rgb: Optional[bool] = None, reuse_coarse: Optional[bool] = None):
+                  t_rand=None, u_rand=None, coarse_rgb: Optional[bool] = None, reuse_coarse: Optional[bool] = None,
+                  fused: Optional[bool] = None):
     """Returns (rgb_map (...,3), depth_map (...,1), extras) like src/render.py:92-97.
 
     `background_color` is accepted and ignored, as in the reference (src/render.py:6).  `t_rand` (B,N) / `u_rand`
@@ -84,7 +122,10 @@ def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
     values (closer to fp32 than the fp16 re-evaluation they replace).  Under autograd the same holds for the backward
     (ReuseRenderFn: every depth goes through the MLP backward once; the gradients equal the two-pass form's, where the
     coarse depths are evaluated twice and the two contributions summed).  (coarse, fine) pairs always evaluate every
-    depth in the fine pass."""
+    depth in the fine pass.
+    `fused` (default ON; NERFW_FUSED_RENDER=0 or fused=False turns it off): when no gradient is recorded, a single-pass or
+    re-use render is ONE library call (nerfw_volume_render: the same launches in the same order, bit-identical outputs,
+    a sixth of the host time per call -- what the reference's 4096-ray chunk loop is made of)."""
     coarse, fine = (model if isinstance(model, (tuple, list)) else (model, model))
     if fine_pass is None:
         fine_pass = os.environ.get("NERFW_COARSE_ONLY", "0") != "1"
@@ -96,19 +137,24 @@ def volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance,
     o = rays_o.to(dev, torch.float32).reshape(-1, 3).contiguous()
     d = rays_d.to(dev, torch.float32).reshape(-1, 3).contiguous()
     b = o.shape[0]
-    d = ops.normalize_dirs(d)                                              # src/render.py:19
     emb = coarse._prep_emb(appearance_embedding, b, dev)                   # src/render.py:33-46
     ztab = ops.depth_table(near, far, n_samples, dev)
     tr = None
     if perturb:
         tr = t_rand.to(dev).reshape(b, n_samples) if t_rand is not None else torch.rand((b, n_samples), device=dev, generator=generator)
-    z, _ = ops.stratified(None, None, ztab, tr, b, want_pts=False)         # src/render.py:22 (pts never materialised)
     hier = n_importance > 0 and fine_pass
     if coarse_rgb is None:
         coarse_rgb = torch.is_grad_enabled()
     if reuse_coarse is None:
         reuse_coarse = os.environ.get("NERFW_REUSE_COARSE", "1") != "0"
     reuse_coarse = bool(reuse_coarse) and hier and coarse is fine
+    if fused is None:
+        fused = os.environ.get("NERFW_FUSED_RENDER", "1") != "0"
+    if fused and b > 0 and (reuse_coarse or not hier) and not _records_gradients(coarse, emb):
+        return _render_fused(coarse, o, d, ztab, tr, int(n_importance) if hier else 0, u_rand, generator, emb, mlp_dtype,
+                             orig_shape, src_dev)
+    d = ops.normalize_dirs(d)                                              # src/render.py:19
+    z, _ = ops.stratified(None, None, ztab, tr, b, want_pts=False)         # src/render.py:22 (pts never materialised)
     if reuse_coarse:
         return _render_reusing_coarse(coarse, o, d, z, emb, mlp_dtype, int(n_importance), u_rand, generator, orig_shape, src_dev)
     sigma_only = hier and not coarse_rgb and not torch.is_grad_enabled()

@@ -201,6 +201,38 @@ int nerfw_composite_bwd(const float* raw, const float* z, int64_t n_rays, int n_
                         const float* d_depth, const float* d_acc, const float* d_weights, float* d_raw,
                         void* stream);
 
+/* ---- volume_render(model, rays_o, rays_d, near, far, n_samples, n_importance, appearance_embedding, ...)
+ * -- src/render.py:5-97, inference (no gradients), as ONE call.  It enqueues exactly the launches of the entry points
+ * above, in the order the reference's function performs the steps: F.normalize of the directions (:19),
+ * sample_stratified (:22), the MLP on the N coarse depths (:29-53), compositing (:56-80) and -- when n_importance > 0,
+ * with one network for both passes -- sample_importance (src/ray_utils.py:90-149), the MLP on the NI new depths,
+ * nerfw_merge_raw and compositing of the merged row.  Outputs are bit-identical to the call-by-call sequence; what the
+ * call saves is host time per invocation (the reference renders a frame as 157 chunks of 4096 rays,
+ * render_aligned_spiral.py:136-155).
+ * rays_d need not be normalised.  ztab / t_rand as for nerfw_stratified, u_lin / u_rand as for nerfw_sample_pdf (unused
+ * when n_importance == 0).  emb: NULL or (emb_rows,32), emb_rows 1 or n_rays.  mode_coarse / mode_fine: NERFW_MLP_* without
+ * flags (n_importance == 0: only mode_coarse is used).
+ * n_importance == 0: rgb, depth, acc, weights (B,N), z_vals (B,N) are written, the *_coarse pointers are ignored.
+ * n_importance  > 0: rgb, depth, acc, weights (B,N+NI), z_vals (B,N+NI) hold the final result and rgb_coarse, depth_coarse,
+ * acc_coarse, weights_coarse (B,N), z_coarse (B,N) the coarse pass's. */
+typedef struct NerfwRenderOut {
+  float* rgb;            /* (B,3) */
+  float* depth;          /* (B,1) */
+  float* acc;            /* (B,1) */
+  float* weights;        /* (B,N+NI) */
+  float* z_vals;         /* (B,N+NI) */
+  float* rgb_coarse;     /* (B,3) */
+  float* depth_coarse;   /* (B,1) */
+  float* acc_coarse;     /* (B,1) */
+  float* weights_coarse; /* (B,N) */
+  float* z_coarse;       /* (B,N) */
+} NerfwRenderOut;
+size_t nerfw_volume_render_workspace_bytes(int64_t n_rays, int n_samples, int n_importance, int64_t emb_rows);
+int nerfw_volume_render(const NerfwWeights* w, const void* packed, const float* rays_o, const float* rays_d,
+                        int64_t n_rays, const float* ztab, const float* t_rand, int n_samples, const float* u_lin,
+                        const float* u_rand, int n_importance, const float* emb, int64_t emb_rows, int mode_coarse,
+                        int mode_fine, const NerfwRenderOut* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- optimizer: torch.optim.Adam.step as used at src/train.py:33-39,92 (no weight decay, no amsgrad) ---
  * One fused launch over a flat parameter buffer.  step is 1-based. grad_scale multiplies g first
  * (1/world_size after the data-parallel all-reduce). */

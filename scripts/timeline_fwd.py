@@ -29,5 +29,5 @@ print("cycles relative to pe_ready seen by the MMA thread (tile 3 of CTA 0)")
 for layer in range(8):
     row = [(names[i], t[10 + layer * 8 + i] - t0 if t[10 + layer * 8 + i] else None) for i in range(8)]
     print(f"layer {layer}: " + "  ".join(f"{k}={v}" for k, v in row))
-for slot, name in ((90, "epi: encodings for next tile written"), (91, "epi: dir acc complete seen"), (92, "epi: dir acc in regs"), (93, "epi: tile written")):
+for slot, name in ((94, "mma: direction layer issued"), (90, "epi: encodings for next tile written"), (91, "epi: dir acc complete seen"), (92, "epi: dir acc in regs"), (93, "epi: tile written")):
     print(f"{name}: {t[slot] - t0 if t[slot] else None}")

@@ -404,3 +404,76 @@ def test_reuse_coarse_equals_two_pass(cuda_model, oracle, golden):
                                    mlp_dtype="bf16x3", u_rand=ub, reuse_coarse=False)
     assert big[2]["z_vals"].shape == (8, 4096) and bool(torch.isfinite(big[0]).all())
     assert torch.equal(big[0], big2[0]) and torch.equal(big[1], big2[1])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "mixed", "bf16"])
+def test_fused_call_equals_call_by_call(cuda_model, oracle, mode):
+    """nerfw_volume_render (one library call per render, the inference default) launches the same kernels in the same order
+    as the call-by-call path: every output is bit-identical -- hierarchical with re-use and single pass, shared / per-ray /
+    no embedding, jittered depths, ragged ray counts."""
+    import nerfw
+    model, emb = cuda_model
+    o, d = view(oracle)
+    gen = torch.Generator().manual_seed(11)
+    for b, rows in ((1000, 1), (129, 0), (777, 777), (1, 1)):
+        oc = o.reshape(-1, 3)[1234:1234 + b]
+        dc = d.reshape(-1, 3)[1234:1234 + b] * 1.7          # not normalised: the call normalises like src/render.py:19
+        e = None if rows == 0 else (emb if rows == 1 else torch.randn(rows, 32, generator=gen).cuda())
+        t = torch.rand(b, 64, generator=gen)
+        u = torch.rand(b, 128, generator=gen)
+        for ni, fine in ((128, True), (128, False), (0, True)):
+            for perturb in (False, True):
+                kw = dict(appearance_embedding=e, perturb=perturb, t_rand=t if perturb else None, u_rand=u, mlp_dtype=mode,
+                          fine_pass=fine)
+                with torch.no_grad():
+                    a = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, ni, fused=False, **kw)
+                    f = nerfw.volume_render(model, oc, dc, 2.0, 6.0, 64, ni, fused=True, **kw)
+                assert torch.equal(a[0], f[0]) and torch.equal(a[1], f[1])
+                assert set(a[2]) == set(f[2]), (sorted(a[2]), sorted(f[2]))
+                for k in a[2]:
+                    assert a[2][k].shape == f[2][k].shape and torch.equal(a[2][k], f[2][k]), (k, b, rows, ni, fine, perturb)
+    # gradients recorded -> never the fused call (it has no backward); CPU rays come back on the CPU
+    with torch.enable_grad():
+        rgb, _, _ = nerfw.volume_render(model, o.reshape(-1, 3)[:64], d.reshape(-1, 3)[:64], 2.0, 6.0, 64, 128,
+                                        appearance_embedding=emb, mlp_dtype=mode)
+        assert rgb.requires_grad
+    with torch.no_grad():
+        rgb, depth, ex = nerfw.volume_render(model, o.reshape(-1, 3)[:64].cpu(), d.reshape(-1, 3)[:64].cpu(), 2.0, 6.0, 64, 128,
+                                             appearance_embedding=emb, perturb=False, mlp_dtype=mode)
+    assert rgb.device.type == "cpu" and depth.device.type == "cpu" and ex["z_vals"].device.type == "cpu"
+
+
+def test_volume_render_abi_errors(cuda_model):
+    """Raw C-ABI behaviour of nerfw_volume_render: too small a workspace, missing coarse outputs, zero rays."""
+    import ctypes as C
+    from nerfw import _lib, ops
+    model, emb = cuda_model
+    lib = _lib.lib()
+    b, n, ni = 256, 64, 128
+    need = lib.nerfw_volume_render_workspace_bytes(b, n, ni, 1)
+    assert need >= b * (n + ni + ni + n) * 16 and lib.nerfw_volume_render_workspace_bytes(-1, n, ni, 1) == 0
+    ws = model.kernel_state()[2]
+    packed = model.packed_weights()
+    o = torch.zeros(b, 3, device="cuda"); o[:, 2] = 4.0
+    d = torch.nn.functional.normalize(torch.randn(b, 3, device="cuda") * 0.2 + torch.tensor([0.0, 0.0, -1.0], device="cuda"), dim=-1)
+    ztab = ops.depth_table(2.0, 6.0, n, o.device)
+    ulin = ops.u_table(ni, o.device)
+    u = torch.rand(b, ni, device="cuda")
+    buf = torch.empty(need, dtype=torch.uint8, device="cuda")
+    outs = {k: torch.empty(b * (n + ni), device="cuda") for k, _ in _lib.NerfwRenderOut._fields_}
+    out = _lib.NerfwRenderOut()
+    for k, t in outs.items():
+        setattr(out, k, t.data_ptr())
+    args = lambda o_struct, wsb: (C.byref(ws), packed.data_ptr(), o.data_ptr(), d.data_ptr(), b, ztab.data_ptr(), None, n,
+                                  ulin.data_ptr(), u.data_ptr(), ni, emb.reshape(1, 32).contiguous().data_ptr(), 1, 1, 3,
+                                  C.byref(o_struct), buf.data_ptr(), wsb, None)
+    assert lib.nerfw_volume_render(*args(out, need)) == 0
+    assert lib.nerfw_volume_render(*args(out, need - 16)) == -4 and b"workspace" in lib.nerfw_last_error()
+    bad = _lib.NerfwRenderOut()
+    for k, t in outs.items():
+        setattr(bad, k, t.data_ptr())
+    bad.weights_coarse = None
+    assert lib.nerfw_volume_render(*args(bad, need)) == -1 and b"coarse output" in lib.nerfw_last_error()
+    a0 = list(args(out, need)); a0[4] = 0
+    assert lib.nerfw_volume_render(*a0) == 0
+    torch.cuda.synchronize()
