@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
   const int64_t ntiles = (n_total + TM - 1) / TM;
+  // profiling: SM cycles and nanoseconds of CTA 0 over the whole launch (average SM clock, cycles per tile)
+  if (timeline && blockIdx.x == 0 && tid == 0) { timeline[120] = clock64(); timeline[121] = (long long)global_timer_ns(); }
   const int64_t stamp_tile = blockIdx.x == 0 ? 2 * (int64_t)gridDim.x : -1;   // profiling: CTA 0, third tile
   // Split (3-MMA) arithmetic for the direction layer only in training mode: its ReLU gates then match the fp32 forward.
   // For inference the layer runs as a single bf16 MMA -- it only feeds the rgb sigmoid (sigma, hence depth, acc and the
@@ -554,6 +556,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  if (timeline && blockIdx.x == 0 && tid == 0) { timeline[122] = clock64(); timeline[123] = (long long)global_timer_ns(); }
   if (warp == F_MMA_WARP) {
     __syncwarp();
     tmem_dealloc<512>(tmem);
