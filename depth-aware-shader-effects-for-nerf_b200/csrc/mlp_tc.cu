@@ -140,14 +140,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
   const int debug_skip_weights = flags & 1;
   constexpr bool sigma_only = SIGMA;
   constexpr int n_chunks = sigma_only ? N_BIG : N_CHUNKS;
-  // Single-MMA modes (bf16 / fp16) have tensor-pipe time to win at the hand-offs (the split mode issues at the power cap):
-  //  * ENC_FIRST: the K blocks whose A operand is an encoding tile in shared memory (skip part of layer 4, direction part of
-  //    the direction layer) are issued FIRST in their layer -- they need the accumulator but no epilogue output, so they
-  //    run while the previous layer's epilogue is still producing its first operand granule;
-  //  * DIR_ACC: the direction layer accumulates into TMEM columns [384,512) (the A_lo region, unused without the split), so
-  //    layer 0 of the NEXT tile is issued right behind it and the epilogue warps finish that layer 0 -- i.e. restart the
-  //    tensor pipe on layer 1 -- BEFORE they turn to the direction-layer accumulator and the rgb head of the previous tile.
-  constexpr bool ENC_FIRST = !X3;
+  // Hand-off scheduling (the tensor pipe idles between the last MMA of a layer and the first of the next; these shorten it):
+  //  * the K blocks whose A operand is an encoding tile in shared memory (skip part of layer 4, direction part of the
+  //    direction layer) are issued FIRST in their layer -- they need the accumulator but no epilogue output, so they run
+  //    while the previous layer's epilogue is still producing its first operand granule;
+  //  * DIR_ACC (single-MMA modes): the direction layer accumulates into TMEM columns [384,512) (the A_lo region, unused
+  //    without the split), so layer 0 of the NEXT tile is issued right behind it and the epilogue warps finish that layer 0
+  //    -- i.e. restart the tensor pipe on layer 1 -- BEFORE they turn to the direction-layer accumulator and the rgb head of
+  //    the previous tile;
+  //  * split mode (no free TMEM columns): the direction accumulator is reduced to the three rgb partial sums at once, and the
+  //    rest of that epilogue (exchange, sigmoid, output store) waits until the next tile's layer 0 has been handed on.
   constexpr bool DIR_ACC = !X3 && !SIGMA;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -211,10 +213,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       RingPipe p;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int j = 0; j < n_chunks; ++j) {
-          // consumption order of the MMA thread: with ENC_FIRST the encoding chunk of layer 4 / the direction layer leads
+          // consumption order of the MMA thread: the encoding chunk of layer 4 / of the direction layer leads its layer
           int i = j;
-          if (ENC_FIRST && j >= 13 && j < 18) i = j == 13 ? 17 : j - 1;
-          if (ENC_FIRST && j >= N_BIG) i = j == N_BIG ? N_CHUNKS - 1 : j - 1;
+          if (j >= 13 && j < 18) i = j == 13 ? 17 : j - 1;
+          if (j >= N_BIG) i = j == N_BIG ? N_CHUNKS - 1 : j - 1;
           const uint32_t sz = i < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
           const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
           for (int v = 0; v < copies; ++v) {
@@ -299,16 +301,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           wait_bar(acc_free, ph_free);
           ph_free ^= 1;
           NERFW_STAMP(10 + layer * 8);
-          const bool skip = layer == NERFW_SKIP;
-          if (ENC_FIRST && skip) kblock(d_acc, false, pex_hi, pex_lo, idesc256, 4, true);
+          if (layer == NERFW_SKIP) kblock(d_acc, false, pex_hi, pex_lo, idesc256, 4, true);
           for (int kb = 0; kb < 4; ++kb) {
             wait_bar(&a_kb[kb], ph_kb);
             if (kb == 0) NERFW_STAMP(11 + layer * 8);   // first operand K block seen
             if (kb == 3) NERFW_STAMP(12 + layer * 8);   // last operand K block seen
-            kblock(d_acc, true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc256, 4, kb == 0 && !(ENC_FIRST && skip));
+            kblock(d_acc, true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc256, 4, kb == 0 && layer != NERFW_SKIP);
           }
           ph_kb ^= 1;
-          if (!ENC_FIRST && skip) kblock(d_acc, false, pex_hi, pex_lo, idesc256, 4, false);
           mma_commit(acc_full);
           NERFW_STAMP(13 + layer * 8);
         }
@@ -321,13 +321,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           wait_bar(acc_free, ph_free);
           ph_free ^= 1;
         }
-        if (ENC_FIRST) kblock(d_dir, false, ped_hi, ped_lo, idesc128, 2, true, dir_split);
+        kblock(d_dir, false, ped_hi, ped_lo, idesc128, 2, true, dir_split);
         for (int kb = 0; kb < 4; ++kb) {
           wait_bar(&a_kb[kb], ph_kb);
-          kblock(d_dir, true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, kb == 0 && !ENC_FIRST, dir_split);
+          kblock(d_dir, true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, false, dir_split);
         }
         ph_kb ^= 1;
-        if (!ENC_FIRST) kblock(d_dir, false, ped_hi, ped_lo, idesc128, 2, false, dir_split);
         mma_commit(DIR_ACC ? acc2_full : acc_full);
         NERFW_STAMP(94);                     // direction layer issued
         if (DIR_ACC && tile + gridDim.x < ntiles) {
@@ -381,12 +380,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         fence_proxy_async_smem();   // ordered before this warp's later a_kb arrivals, which the MMA thread waits on
       }
     };
-    // ---- direction-layer epilogue + rgb head of one tile (src/models.py:141-160).  DIR_ACC: the layer has its own accumulator
-    // and barriers, and the call for tile t is made from inside tile t+1, after its layer-0 epilogue (see the tile loop).
+    // ---- direction-layer epilogue + rgb head of one tile (src/models.py:141-160), in two parts.  Part A pulls the accumulator
+    // and reduces it to this thread's three rgb partial sums; part B exchanges them, applies the sigmoid and stores the
+    // sample.  Part B of tile t always runs inside tile t+1, after its layer-0 epilogue, i.e. with the tensor pipe already
+    // restarted on layer 1; DIR_ACC (own accumulator and barriers) moves part A there as well.
     uint32_t acc2_phase = 0;
-    auto dir_epilogue = [&](int64_t tile) {
-      const int64_t s = tile * TM + row;
-      const bool live = s < n_total;
+    float p3[3] = {0.f, 0.f, 0.f};
+    auto dir_part_a = [&](int64_t tile) {
       if (DIR_ACC) {
         mbar_wait(acc2_full, acc2_phase);
         acc2_phase ^= 1;
@@ -396,36 +396,38 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       }
       tc_fence_after();
       if (tid == 0) NERFW_STAMP(91);   // direction-layer accumulator complete seen
-      float p3[3] = {0.f, 0.f, 0.f};
-      {
-        const uint32_t col = cq * 32;
-        uint32_t r[32];
-        tmem_ld32(tlane + (DIR_ACC ? COL_ALO : COL_ACC) + col, r);
-        tmem_wait_ld();
-        tc_fence_before();
-        mbar_arrive_warp(DIR_ACC ? acc2_free : acc_free);   // the next direction layer / the next tile's layer 0 may start
-        if (tid == 0) NERFW_STAMP(92);
-        uint32_t bits = 0;
-        // bias and rgb-head rows as 16-byte shared-memory loads (a quarter of the wavefronts of scalar loads: this epilogue
-        // runs next to the MMAs of the following tile's layer 1, which read their B operand through the same pipe)
-        const float4* b4 = reinterpret_cast<const float4*>(vec + V_DIRB + col);
-        const float4* w4 = reinterpret_cast<const float4*>(vec + V_RGBW + col);
+      p3[0] = p3[1] = p3[2] = 0.f;
+      const uint32_t col = cq * 32;
+      uint32_t r[32];
+      tmem_ld32(tlane + (DIR_ACC ? COL_ALO : COL_ACC) + col, r);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive_warp(DIR_ACC ? acc2_free : acc_free);   // the next direction layer / the next tile's layer 0 may start
+      if (tid == 0) NERFW_STAMP(92);
+      uint32_t bits = 0;
+      // bias and rgb-head rows as 16-byte shared-memory loads (a quarter of the wavefronts of scalar loads: this epilogue
+      // runs next to MMAs of the following tile, which read their B operand through the same pipe)
+      const float4* b4 = reinterpret_cast<const float4*>(vec + V_DIRB + col);
+      const float4* w4 = reinterpret_cast<const float4*>(vec + V_RGBW + col);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bb = b4[j4], wr = w4[j4], wg = w4[32 + j4], wb = w4[64 + j4];
-          const float bj[4] = {bb.x, bb.y, bb.z, bb.w};
-          const float wj[3][4] = {{wr.x, wr.y, wr.z, wr.w}, {wg.x, wg.y, wg.z, wg.w}, {wb.x, wb.y, wb.z, wb.w}};
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 bb = b4[j4], wr = w4[j4], wg = w4[32 + j4], wb = w4[64 + j4];
+        const float bj[4] = {bb.x, bb.y, bb.z, bb.w};
+        const float wj[3][4] = {{wr.x, wr.y, wr.z, wr.w}, {wg.x, wg.y, wg.z, wg.w}, {wb.x, wb.y, wb.z, wb.w}};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = 4 * j4 + e;
-            float hv = fmaxf(__uint_as_float(r[j]) + bj[e], 0.f);
-            bits |= (hv > 0.f ? 1u : 0u) << j;
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * j4 + e;
+          float hv = fmaxf(__uint_as_float(r[j]) + bj[e], 0.f);
+          bits |= (hv > 0.f ? 1u : 0u) << j;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv, wj[c][e], p3[c]);
-          }
+          for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv, wj[c][e], p3[c]);
         }
-        if (masks) masks[mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))] = bits;
       }
+      if (masks) masks[mask_index(tile, NERFW_LAYERS, row, cq >> 1, (int)(cq & 1))] = bits;
+    };
+    auto dir_part_b = [&](int64_t tile) {
+      const int64_t s = tile * TM + row;
+      const bool live = s < n_total;
       if (cq != 0) rgb_part[cq * TM + row] = make_float4(p3[0], p3[1], p3[2], 0.f);
       named_bar_sync(1, F_EPI_THREADS);
       if (cq == 0 && live) {
@@ -526,10 +528,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           if (tid == 0 && kb == 0) NERFW_STAMP(16 + layer * 8);
           if (tid == 0 && kb == 3) NERFW_STAMP(17 + layer * 8);
         }
-        // DIR_ACC: layer 1's first operand block is out and the tensor pipe busy again: now finish the PREVIOUS tile
-        // (its sig_part / direction accumulator are untouched until this tile's layer 7 / direction layer)
-        if (DIR_ACC && layer == 0 && pending >= 0) {
-          dir_epilogue(pending);
+        // layer 1's operand is out and the tensor pipe busy again: now finish the PREVIOUS tile (its sig_part, rgb partial
+        // sums and -- DIR_ACC -- direction accumulator are untouched until this tile's layer 7 / direction layer)
+        if (layer == 0 && pending >= 0) {
+          if (DIR_ACC) dir_part_a(pending);
+          dir_part_b(pending);
           pending = -1;
         }
         if (layer == NERFW_SKIP + 1) {
@@ -548,10 +551,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
         continue;
       }
 
-      if (DIR_ACC) pending = tile;   // finished inside the next tile (or after the loop)
-      else dir_epilogue(tile);
+      if (!DIR_ACC) dir_part_a(tile);   // shared accumulator: free it for the next tile's layer 0 right away
+      pending = tile;                   // the rest inside the next tile (or after the loop)
     }
-    if (DIR_ACC && pending >= 0) dir_epilogue(pending);
+    if (pending >= 0) {
+      if (DIR_ACC) dir_part_a(pending);
+      dir_part_b(pending);
+    }
   }
   // ---- teardown ----
   tc_fence_before();
