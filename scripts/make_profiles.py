@@ -29,7 +29,7 @@ for mode in ("mixed", "bf16x3", "bf16"):
     raw = os.path.join(OUT, f"prof_frame_{mode}_raw.csv")
     if os.path.exists(raw):
         write(f"{TAG}_ncu_full_{mode}.md",
-              f"# Round {int(TAG[1:])} (final kernels) — ncu --set full, 200-row crop of the 800x800 frame (160 000 rays, 64 + 192 samples), {mode} mode\n\n"
+              f"# Round {int(TAG[1:])} (final kernels) — ncu --set full, 200-row crop of the 800x800 frame (160 000 rays; coarse pass 64 depths, fine pass the 128 new depths), {mode} mode\n\n"
               f"Command: {CMD.format('profile_frame.py --mode ' + mode + ' --rows 200')}.  The two mlp_tc_fwd launches = coarse / fine pass.\n\n"
               + run("ncu_summary.py", raw))
     src = os.path.join(OUT, f"prof_frame_{mode}_src_mlp_tc_fwd.csv")
