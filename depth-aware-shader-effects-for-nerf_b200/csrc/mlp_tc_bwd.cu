@@ -417,8 +417,13 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
               reinterpret_cast<unsigned short*>(mask_words(sm, layer, row))[col >> 4] = (unsigned short)bits;
             }
             if (layer == NERFW_LAYERS - 1) {
+              const float4* w4 = reinterpret_cast<const float4*>(vec + V_DENW + col);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) sig = fmaf(fmaxf(a[e], 0.f), vec[V_DENW + col + e], sig);
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 ww = w4[e4];
+                sig = fmaf(fmaxf(a[4 * e4], 0.f), ww.x, sig); sig = fmaf(fmaxf(a[4 * e4 + 1], 0.f), ww.y, sig);
+                sig = fmaf(fmaxf(a[4 * e4 + 2], 0.f), ww.z, sig); sig = fmaf(fmaxf(a[4 * e4 + 3], 0.f), ww.w, sig);
+              }
             }
           }
           const uint32_t p8[8] = {ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]};
@@ -453,16 +458,32 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
         mbar_arrive_warp(acc_free);
         uint32_t bits = 0;
         float hv[32];
+        // bias, rgb-head rows and the appearance vector as 16-byte shared-memory loads: this step is on the critical path of
+        // the tile (the tensor pipe waits for its dZ operand) and scalar loads made it LSU-bound (224 wavefronts per warp)
+        const float4* b4 = reinterpret_cast<const float4*>(vec + V_DIRB + dcol);
+        const float4* w4 = reinterpret_cast<const float4*>(vec + V_RGBW + dcol);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          hv[j] = fmaxf(__uint_as_float(r[j]) + vec[V_DIRB + dcol + j], 0.f);
-          bits |= (hv[j] > 0.f ? 1u : 0u) << j;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bb = b4[j4], wr = w4[j4], wg = w4[32 + j4], wb = w4[64 + j4];
+          const float bj[4] = {bb.x, bb.y, bb.z, bb.w};
+          const float wj[3][4] = {{wr.x, wr.y, wr.z, wr.w}, {wg.x, wg.y, wg.z, wg.w}, {wb.x, wb.y, wb.z, wb.w}};
 #pragma unroll
-          for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv[j], vec[V_RGBW + c * 128 + dcol + j], p3[c]);
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * j4 + e;
+            hv[j] = fmaxf(__uint_as_float(r[j]) + bj[e], 0.f);
+            bits |= (hv[j] > 0.f ? 1u : 0u) << j;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p3[c] = fmaf(hv[j], wj[c][e], p3[c]);
+          }
         }
         if (src.emb_shared || !app_vec) {
+          const float4* a4p = reinterpret_cast<const float4*>(appv + dcol);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) ph_hdt[j] = pack_bf16x2(hv[2 * j] + appv[dcol + 2 * j], hv[2 * j + 1] + appv[dcol + 2 * j + 1]);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 a4 = a4p[j4];
+            ph_hdt[2 * j4] = pack_bf16x2(hv[4 * j4] + a4.x, hv[4 * j4 + 1] + a4.y);
+            ph_hdt[2 * j4 + 1] = pack_bf16x2(hv[4 * j4 + 2] + a4.z, hv[4 * j4 + 3] + a4.w);
+          }
         } else {  // per-ray embeddings: a = W_app e_ray + b_app, one 128-float row per ray (app_vec_kernel)
           const float4* av = reinterpret_cast<const float4*>(app_vec + (live ? src.emb_row(s) : 0) * NERFW_DIR_HIDDEN + dcol);
 #pragma unroll
@@ -530,12 +551,16 @@ __global__ void __launch_bounds__(P1_THREADS, 1) mlp_tc_bwd_pass1_kernel(const u
       }
       {
         uint32_t ph[16];
+        const float4* w4 = reinterpret_cast<const float4*>(vec + V_RGBW + dcol);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t c0 = dcol + 2 * j;
-          const float g0 = dlog[0] * vec[V_RGBW + c0] + dlog[1] * vec[V_RGBW + 128 + c0] + dlog[2] * vec[V_RGBW + 256 + c0];
-          const float g1 = dlog[0] * vec[V_RGBW + c0 + 1] + dlog[1] * vec[V_RGBW + 128 + c0 + 1] + dlog[2] * vec[V_RGBW + 256 + c0 + 1];
-          ph[j] = gate_pack(g0, g1, hmask, j);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 wr = w4[j4], wg = w4[32 + j4], wb = w4[64 + j4];
+          const float g0 = dlog[0] * wr.x + dlog[1] * wg.x + dlog[2] * wb.x;
+          const float g1 = dlog[0] * wr.y + dlog[1] * wg.y + dlog[2] * wb.y;
+          const float g2 = dlog[0] * wr.z + dlog[1] * wg.z + dlog[2] * wb.z;
+          const float g3 = dlog[0] * wr.w + dlog[1] * wg.w + dlog[2] * wb.w;
+          ph[2 * j4] = gate_pack(g0, g1, hmask, 2 * j4);
+          ph[2 * j4 + 1] = gate_pack(g2, g3, hmask, 2 * j4 + 1);
         }
         tmem_st16(tlane + COL_AHI + (dcol >> 1), ph);   // K = direction-layer feature, natural order (2 K blocks)
         tmem_wait_st();
