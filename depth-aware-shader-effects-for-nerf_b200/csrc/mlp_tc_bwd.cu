@@ -1023,7 +1023,8 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_mn_kernel(const __nv_bfl
 }
 
 // Issue-rate probe: `reps` x 16 MMAs (M=128, N, K=16) over resident operand tiles, cycles measured with clock64.
-// mode 0: K-major SS, 1: K-major TS (A in TMEM), 2: MN-major SS.  Operand contents are irrelevant (zeros).
+// mode 0: K-major SS, 1: K-major TS (A in TMEM), 2: MN-major SS; 3 / 4: kind::i8 (s8 x s8 -> s32, K = 32) SS / TS; 5: kind::f8f6f4
+// (e4m3, K = 32) SS.  Operand contents are irrelevant (zeros).
 __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int mode, int N, int reps, long long* __restrict__ cycles) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -1040,15 +1041,24 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int mode, int N, int 
   const uint32_t tmem = *tmem_ptr;
   if (tid == 0) {
     const uint32_t sa = smem_u32(sm), sb = smem_u32(sm + 65536);
+    // the mode is dispatched OUTSIDE the issue loop: a six-way branch per instruction would itself bound the measured rate
+    const uint32_t n32 = (uint32_t)N;
+    auto run = [&](auto issue) {
+      for (int r = 0; r < reps; ++r)
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) issue(kb, k);
+    };
     long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) {
-      for (int kb = 0; kb < 4; ++kb) {
-        for (int k = 0; k < 4; ++k) {
-          if (mode == 0) mma_ss(tmem, smem_desc_sw128(sa + kb * 16384) + 2 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_bf16(128, (uint32_t)N), 1u);
-          else if (mode == 1) mma_ts(tmem, tmem + COL_AHI + 32 * kb + 8 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_bf16(128, (uint32_t)N), 1u);
-          else mma_ss(tmem, smem_desc_sw128_mn(sa, 8192) + 128 * (kb * 4 + k) % 512, smem_desc_sw128_mn(sb, 8192) + 128 * ((kb * 4 + k) % 4), idesc_bf16_mn(128, (uint32_t)N), 1u);
-        }
-      }
+    switch (mode) {
+      case 0: run([&](int kb, int k) { mma_ss(tmem, smem_desc_sw128(sa + kb * 16384) + 2 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_bf16(128, n32), 1u); }); break;
+      case 1: run([&](int kb, int k) { mma_ts(tmem, tmem + COL_AHI + 32 * kb + 8 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_bf16(128, n32), 1u); }); break;
+      case 2: run([&](int kb, int k) { mma_ss(tmem, smem_desc_sw128_mn(sa, 8192) + 128 * (kb * 4 + k) % 512, smem_desc_sw128_mn(sb, 8192) + 128 * ((kb * 4 + k) % 4), idesc_bf16_mn(128, n32), 1u); }); break;
+      // 8-bit kinds: 128 x N x 32 per instruction (twice the K of the 16-bit kinds over the same 32 operand bytes per row)
+      case 3: run([&](int kb, int k) { mma_ss_i8(tmem, smem_desc_sw128(sa + kb * 16384) + 2 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_s8(128, n32), 1u); }); break;
+      case 4: run([&](int kb, int k) { mma_ts_i8(tmem, tmem + COL_AHI + 32 * kb + 8 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_s8(128, n32), 1u); }); break;
+      default: run([&](int kb, int k) { mma_ss_f8(tmem, smem_desc_sw128(sa + kb * 16384) + 2 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_f16(128, n32), 1u); }); break;
     }
     mma_commit(bar);
     mbar_wait(bar, 0);
@@ -1267,7 +1277,7 @@ extern "C" int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, 
 
 // Tensor-pipe issue-rate probe (tests / DESIGN.md numbers): cycles for reps x 16 MMAs of shape 128 x n x 16.
 extern "C" int nerfw_selftest_umma_rate(int mode, int n, int reps, long long* cycles_dev, void* stream) {
-  NERFW_REQUIRE(cycles_dev && mode >= 0 && mode <= 2 && n >= 16 && n <= 256 && n % 16 == 0 && reps >= 1, "nerfw_selftest_umma_rate: bad arguments");
+  NERFW_REQUIRE(cycles_dev && mode >= 0 && mode <= 5 && n >= 16 && n <= 256 && n % 16 == 0 && reps >= 1, "nerfw_selftest_umma_rate: bad arguments");
   const size_t smem = 65536 + 131072 + 64 + 1024;
   static thread_local unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {

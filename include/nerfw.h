@@ -287,7 +287,8 @@ int nerfw_selftest_umma(const void* a_bf16, const void* b_bf16, int n, int k, in
 /* Same with both operands MN-major (the wgrad form): D (128,n) = At^T Bt for At (k,128), Bt (k,n) bf16 row-major. */
 int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, int n, int k, float* d, void* stream);
 /* Tensor-pipe issue-rate probe: device cycles (int64 at cycles_dev) for reps x 16 MMAs of shape 128 x n x 16;
- * mode 0 = K-major smem operands, 1 = A from tensor memory, 2 = both operands MN-major. */
+ * mode 0 = K-major smem operands, 1 = A from tensor memory, 2 = both operands MN-major (kind::f16); 3 / 4 = kind::i8
+ * (s8 x s8 -> s32, 128 x n x 32 per instruction) with A from shared / tensor memory, 5 = kind::f8f6f4 (e4m3), shared memory. */
 int nerfw_selftest_umma_rate(int mode, int n, int reps, long long* cycles_dev, void* stream);
 
 #ifdef __cplusplus

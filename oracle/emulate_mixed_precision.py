@@ -58,6 +58,20 @@ def make_linear(scheme):
             c1 = f8(lox * 2.0 ** sa, torch.float8_e4m3fn, 448.0).double() @ f8(w * 2.0 ** -sa, torch.float8_e5m2, 57344.0).double().T
             c2 = f8(x * 2.0 ** -sw, torch.float8_e5m2, 57344.0).double() @ f8(low * 2.0 ** sw, torch.float8_e4m3fn, 448.0).double().T
             y = x16.double() @ w16.double().T + c1 + c2
+        elif scheme in ("fp16_i8c", "bf16_i8c"):
+            # main term in fp16 (bf16), both first-order correction terms as ONE int8 x int8 -> int32 accumulation
+            # (kind::i8 issues at twice the fp16 rate: 2 instead of 3 MMA units per product).  Per-row power-of-two scales
+            # sx_i (activations) and sw_j (weight rows); the residuals are quantised with the scales sx_i 2^-q, sw_j 2^-q
+            # (q = 11 for fp16, 8 for bf16: |lo| <= 2^-(q+1) |value|), so both products carry the scale sx_i sw_j 2^-q and can
+            # share an integer accumulator:  x w ~ x16 w16 + sx sw 2^-q (Q(lo_x) Q(w)^T + Q(x) Q(lo_w)^T).
+            dt, q = (torch.float16, 11) if scheme == "fp16_i8c" else (torch.bfloat16, 8)
+            xm, wm = rnd(x, dt), rnd(w, dt)
+            lox, low = x - xm, w - wm
+            p2 = lambda t: torch.exp2(torch.ceil(torch.log2(t.abs().amax(-1, keepdim=True).clamp_min(1e-30) / 127.0)))
+            sx, sw = p2(x), p2(w)
+            qi = lambda t, sc: torch.round(t / sc).clamp(-127, 127)
+            corr = qi(lox, sx * 2.0 ** -q).double() @ qi(w, sw).double().T + qi(x, sx).double() @ qi(low, sw * 2.0 ** -q).double().T
+            y = xm.double() @ wm.double().T + corr * (sx.double() * sw.double().T * 2.0 ** -q)
         else:
             raise ValueError(scheme)
         return (y + b.double()).float()
