@@ -218,6 +218,24 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           if (j >= 13 && j < 18) i = j == 13 ? 17 : j - 1;
           if (j >= N_BIG) i = j == N_BIG ? N_CHUNKS - 1 : j - 1;
           const uint32_t sz = i < N_BIG ? BIG_CHUNK : SMALL_CHUNK;
+          if (!sigma_only && !dir_split && j > N_BIG) {
+            // unsplit direction layer: its four 16 KB hidden K blocks travel two per ring stage (one full / empty hand-shake
+            // per eight N = 128 MMAs: at four, the hand-shake, not the tensor pipe, sets the pace -- umma_rate mode 6)
+            if ((j - N_BIG) & 1) {   // j = N_BIG + 1, N_BIG + 3: chunks (30, 31), (32, 33)
+              mbar_wait(&empty[p.stage], p.phase ^ 1);
+              if (debug_skip_weights && tile != (int64_t)blockIdx.x) {
+                mbar_arrive(&full[p.stage]);
+              } else {
+                mbar_arrive_expect_tx(&full[p.stage], 2 * SMALL_CHUNK);
+                for (int q = 0; q < 2; ++q) {
+                  const uint8_t* srcw = F16 ? packed + f16_offset + chunk_offset_f16(i + q) : packed + chunk_offset(i + q);
+                  bulk_g2s(sm + RING + p.stage * BIG_CHUNK + q * SMALL_CHUNK, srcw, SMALL_CHUNK, &full[p.stage]);
+                }
+              }
+              p.advance();
+            }
+            continue;
+          }
           const int copies = (X3 && (i < N_BIG || dir_split)) ? 2 : 1;
           for (int v = 0; v < copies; ++v) {
             mbar_wait(&empty[p.stage], p.phase ^ 1);
@@ -322,9 +340,25 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           ph_free ^= 1;
         }
         kblock(d_dir, false, ped_hi, ped_lo, idesc128, 2, true, dir_split);
-        for (int kb = 0; kb < 4; ++kb) {
-          wait_bar(&a_kb[kb], ph_kb);
-          kblock(d_dir, true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, false, dir_split);
+        if (dir_split) {
+          for (int kb = 0; kb < 4; ++kb) {
+            wait_bar(&a_kb[kb], ph_kb);
+            kblock(d_dir, true, tmem + COL_AHI + 32 * kb, tmem + COL_ALO + 32 * kb, idesc128, 4, false, true);
+          }
+        } else {
+          // two hidden K blocks per ring stage (see the producer)
+          for (int pr = 0; pr < 2; ++pr) {
+            wait_bar(&a_kb[2 * pr], ph_kb);
+            mbar_wait(&full[p.stage], p.phase);
+            tc_fence_after();
+            const uint64_t b0 = smem_desc_sw128(ring + p.stage * BIG_CHUNK);
+            for (int k = 0; k < 4; ++k) mma_ts(d_dir, tmem + COL_AHI + 32 * (2 * pr) + 8 * k, b0 + 2 * k, idesc128, 1u);
+            wait_bar(&a_kb[2 * pr + 1], ph_kb);
+            const uint64_t b1 = smem_desc_sw128(ring + p.stage * BIG_CHUNK + SMALL_CHUNK);
+            for (int k = 0; k < 4; ++k) mma_ts(d_dir, tmem + COL_AHI + 32 * (2 * pr + 1) + 8 * k, b1 + 2 * k, idesc128, 1u);
+            mma_commit(&empty[p.stage]);
+            p.advance();
+          }
         }
         ph_kb ^= 1;
         mma_commit(DIR_ACC ? acc2_full : acc_full);

@@ -1028,11 +1028,11 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_mn_kernel(const __nv_bfl
 __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int mode, int N, int reps, long long* __restrict__ cycles) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 65536 + 131072);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 65536 + 131072);   // [0] end of run, [2] a completed phase, [3] commit sink
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (65536 + 131072) / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 2, 1); mbar_init(bar + 3, 1); fence_mbar_init(); mbar_arrive(bar + 2); }
   if (warp == 0) tmem_alloc<512>(tmem_ptr);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -1058,6 +1058,19 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int mode, int N, int 
       // 8-bit kinds: 128 x N x 32 per instruction (twice the K of the 16-bit kinds over the same 32 operand bytes per row)
       case 3: run([&](int kb, int k) { mma_ss_i8(tmem, smem_desc_sw128(sa + kb * 16384) + 2 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_s8(128, n32), 1u); }); break;
       case 4: run([&](int kb, int k) { mma_ts_i8(tmem, tmem + COL_AHI + 32 * kb + 8 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_s8(128, n32), 1u); }); break;
+      case 6:   // A from tensor memory with the production kernels' per-K-block protocol around every four instructions:
+                // wait on an (already complete) full barrier, tcgen05 fence, four MMAs, commit to a ring-stage barrier
+        for (int r = 0; r < reps; ++r)
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(bar + 2, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_ts(tmem, tmem + COL_AHI + 32 * kb + 8 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_bf16(128, n32), 1u);
+            mma_commit(bar + 3);
+          }
+        break;
       default: run([&](int kb, int k) { mma_ss_f8(tmem, smem_desc_sw128(sa + kb * 16384) + 2 * k, smem_desc_sw128(sb + kb * BIG_CHUNK) + 2 * k, idesc_f16(128, n32), 1u); }); break;
     }
     mma_commit(bar);
@@ -1277,7 +1290,7 @@ extern "C" int nerfw_selftest_umma_mn(const void* at_bf16, const void* bt_bf16, 
 
 // Tensor-pipe issue-rate probe (tests / DESIGN.md numbers): cycles for reps x 16 MMAs of shape 128 x n x 16.
 extern "C" int nerfw_selftest_umma_rate(int mode, int n, int reps, long long* cycles_dev, void* stream) {
-  NERFW_REQUIRE(cycles_dev && mode >= 0 && mode <= 5 && n >= 16 && n <= 256 && n % 16 == 0 && reps >= 1, "nerfw_selftest_umma_rate: bad arguments");
+  NERFW_REQUIRE(cycles_dev && mode >= 0 && mode <= 6 && n >= 16 && n <= 256 && n % 16 == 0 && reps >= 1, "nerfw_selftest_umma_rate: bad arguments");
   const size_t smem = 65536 + 131072 + 64 + 1024;
   static thread_local unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {
