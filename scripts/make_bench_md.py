@@ -17,11 +17,14 @@ o = [f"# Round {int(TAG[1:])} — bench.py on B200 (copies of gpurun_out/bench_*
      "gradient check and the training step.", "",
      "| GPUs | render Mrays/s (weak) | e2e Mrays/s | ms/frame-step | one frame, strong (ms / Mrays/s) | 120-frame spiral to rank 0 (s / Mrays/s) | train step ms | dp_check |",
      "|---|---|---|---|---|---|---|---|"]
+STALE = {int(x) for x in os.environ.get("BENCH_MD_STALE", "").split(",") if x}   # lines measured with an earlier kernel build
 for n, d in sorted(lines.items()):
     st, sp, dp = d.get("strong_one_frame", {}), d.get("spiral_120", {}), d.get("dp_check")
-    o.append(f"| {n} | {d['value']:.3f} | {d['e2e']['value']:.3f} | {d['ms_per_step']:.1f} | {st.get('ms_per_frame', 0):.1f} / {st.get('value', 0):.2f} | "
+    o.append(f"| {n}{' (*)' if n in STALE else ''} | {d['value']:.3f} | {d['e2e']['value']:.3f} | {d['ms_per_step']:.1f} | {st.get('ms_per_frame', 0):.1f} / {st.get('value', 0):.2f} | "
              f"{sp.get('wall_s', 0):.2f} / {sp.get('value', 0):.2f} | {d['train_step']['ms_per_step']:.2f} | "
              + (f"{dp['rel_max_abs']:.1e}" if dp and 'rel_max_abs' in dp else "n/a") + " |")
+if STALE:
+    o += ["", "(*) measured before the mbarrier waits were given a suspend-time hint (forward tile 32.7k -> 29.4k cycles); not re-run."]
 d = lines.get(1)
 if d:
     r, ro = d["roofline"], d["roofline_other"]
