@@ -39,6 +39,14 @@ def test_host_only_entry_points():
     assert L.nerfw_mlp_workspace_bytes(4096, 1) >= 16
     assert L.nerfw_mlp_workspace_bytes(4096, 4096) >= 16 * 4096
     assert L.nerfw_launch_count() == 0 or L.nerfw_launch_count() > 0
+    # nerfw_volume_render workspace: normalised directions + coarse records [+ new depths, fine records, merged records]
+    # + the MLP's per-embedding-row workspace, every section 16-byte aligned
+    b, n, ni = 4096, 64, 128
+    app = (L.nerfw_mlp_workspace_bytes(b, 1) + 15) // 16 * 16
+    assert L.nerfw_volume_render_workspace_bytes(b, n, 0, 1) == b * 12 + b * n * 16 + app
+    assert L.nerfw_volume_render_workspace_bytes(b, n, ni, 1) == b * 12 + b * n * 16 + b * ni * 4 + b * ni * 16 + b * (n + ni) * 16 + app
+    assert L.nerfw_volume_render_workspace_bytes(3, 7, 5, 0) % 16 == 0     # ragged sizes stay aligned
+    assert L.nerfw_volume_render_workspace_bytes(-1, n, ni, 1) == 0 and L.nerfw_volume_render_workspace_bytes(b, 0, ni, 1) == 0
 
 
 def test_argument_errors_are_reported_before_any_launch():
@@ -52,6 +60,11 @@ def test_argument_errors_are_reported_before_any_launch():
     assert rc == -1
     with pytest.raises(ValueError):
         _lib.check(rc)
+    out = _lib.NerfwRenderOut()
+    rc = L.nerfw_volume_render(None, None, None, None, 4, None, None, 64, None, None, 128, None, 0, 1, 3, ctypes.byref(out), None, 0, None)
+    assert rc == -1 and b"null" in L.nerfw_last_error()
+    assert L.nerfw_volume_render(None, None, None, None, 0, None, None, 64, None, None, 128, None, 0, 1, 3, ctypes.byref(out), None, 0, None) == 0
+    assert L.nerfw_volume_render(None, None, None, None, 4, None, None, 64, None, None, 128, None, 0, 1, 3, None, None, 0, None) == -1
     # empty inputs are a no-op, not an error (reference functions accept empty batches)
     assert L.nerfw_normalize_dirs(None, 0, None, None) == 0
     assert L.nerfw_composite_fwd(None, None, 0, 64, None, None, None, None, None) == 0
