@@ -385,11 +385,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
     // quarter 2 its direction tile.  They are not on the MMA critical path: the position tile of the NEXT sample tile and
     // the direction tile of the current one are filled in between two trunk epilogues, once the skip layer has consumed
     // the position tile, while the tensor pipe works on layer 6.
-    auto encode_pos = [&](int64_t t) {
+    // `pre`: the sample's position / direction fetched ahead of time (top of the tile loop), or nullptr to fetch here
+    auto encode_pos = [&](int64_t t, const float* pre) {
       if (cq < 2) {
         const int64_t sr = t * TM + row;
         float x[3] = {0.f, 0.f, 0.f};
-        if (sr < n_total) src.position(sr, x);
+        if (pre) { x[0] = pre[0]; x[1] = pre[1]; x[2] = pre[2]; }
+        else if (sr < n_total) src.position(sr, x);
         float v[32];
         if (cq == 0) {
           pos_features32<0, !X3>(x, v);
@@ -402,11 +404,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       fence_proxy_async_smem();
       mbar_arrive_warp(pe_ready);
     };
-    auto encode_dir = [&](int64_t t) {
+    auto encode_dir = [&](int64_t t, const float* pre) {
       if (cq == 2) {
         const int64_t sr = t * TM + row;
         float d[3] = {0.f, 0.f, 0.f};
-        if (sr < n_total) src.direction(sr, d);
+        if (pre) { d[0] = pre[0]; d[1] = pre[1]; d[2] = pre[2]; }
+        else if (sr < n_total) src.direction(sr, d);
         float v[32];
         dir_features32<!X3>(d, v);
         if (dir_split) store_features32<true>(ped_hi, sm + SM_PED_LO, row, 0, v);
@@ -479,10 +482,27 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
       if (tid == 0) NERFW_STAMP(93);   // tile written
     };
     int64_t pending = -1;
-    if ((int64_t)blockIdx.x < ntiles) encode_pos(blockIdx.x);
+    if ((int64_t)blockIdx.x < ntiles) encode_pos(blockIdx.x, nullptr);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t s = tile * TM + row;
       const bool live = s < n_total;
+      // Inputs of the encodings written after layer 5 (next tile's positions: quarters 0 / 1; this tile's directions:
+      // quarter 2), fetched now: the 64-bit ray-index division and the global loads are off the path by then -- with the
+      // MMA phases at the pipe's rate the encodings no longer hide behind layer 6 and were delaying its epilogue.
+      // Single-MMA modes only: the split mode's MMA phases are three times as long and still cover the encodings, and
+      // its epilogue has no registers to spare.
+      float pre_v[3] = {0.f, 0.f, 0.f};
+      const float* pre = nullptr;
+      if constexpr (!X3) {
+        if (cq < 2) {
+          const int64_t sr = (tile + gridDim.x) * TM + row;
+          if (tile + gridDim.x < ntiles && sr < n_total) src.position(sr, pre_v);
+        } else if (cq == 2 && !sigma_only) {
+          const int64_t sr = tile * TM + row;
+          if (sr < n_total) src.direction(sr, pre_v);
+        }
+        pre = pre_v;
+      }
       // ---- trunk epilogues: acc -> bias, ReLU -> bf16 (hi[,lo]) -> next layer's A operand in TMEM ----
       float sig = 0.f;
       // Thread <-> (row, accumulator columns 64 cq .. 64 cq + 63).  All 64 values are pulled into registers first and the
@@ -570,8 +590,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mlp_tc_fwd_kernel(const uint8_t*
           pending = -1;
         }
         if (layer == NERFW_SKIP + 1) {
-          if (!sigma_only) encode_dir(tile);
-          if (tile + gridDim.x < ntiles) encode_pos(tile + gridDim.x);
+          if (!sigma_only) encode_dir(tile, pre);
+          if (tile + gridDim.x < ntiles) encode_pos(tile + gridDim.x, pre);
           if (tid == 0) NERFW_STAMP(90);   // encodings written
         }
       }
