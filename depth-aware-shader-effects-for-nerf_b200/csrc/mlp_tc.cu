@@ -14,7 +14,11 @@
 //
 // NERFW_MLP_BF16X3 ("fp32 parity" mode): every operand is split x = hi + lo with hi = bf16(x), lo = bf16(x - hi) and
 // each product is three MMAs  A_hi W_hi + A_lo W_hi + A_hi W_lo  (dropped term ~2^-18): ~2^-16 relative error per
-// product against 2^-9 for plain bf16 and 2^-11 for TF32.  A_lo lives in TMEM columns [384,512).
+// product against 2^-9 for plain bf16 and 2^-11 for TF32.  A_lo lives in TMEM columns [384,512); in the single-MMA
+// modes (bf16, fp16) those columns hold the direction layer's accumulator instead, so that the next tile's layer 0 can
+// be issued behind the direction layer (see DIR_ACC below).
+// Every wait is an mbarrier.try_wait with a suspend-time hint (umma.cuh): a waiting warp sleeps in hardware.  Plain
+// polling loops in the 16 epilogue warps cost the tensor pipe 10 % of its cycles.
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "mlp_common.cuh"
